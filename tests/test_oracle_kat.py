@@ -1,0 +1,30 @@
+"""Pins the oracle against the reference's only golden vectors: the README demo
+(/root/reference/README.md:36-62 objective trace, :101-114 se_scores head)."""
+import json
+import os
+
+import numpy as np
+
+from oracle.scgbm_oracle import get_se
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "readme_demo.json")))
+
+
+def test_r_rng_restatement_shape(readme_Y):
+    assert readme_Y.shape == (500, 500)
+    assert readme_Y.min() == 0 and readme_Y.sum() == 249237
+
+
+def test_readme_objective_trace(readme_oracle_fit):
+    out = readme_oracle_fit
+    acc_iters = (np.nonzero(out["_accepted"])[0] + 1).tolist()
+    assert acc_iters == G["printed_iterations"]          # reverts at 12 and 19 (Q3)
+    assert out["_n_iter"] == 31                          # revert at 30, break at 31
+    printed = ["%.7g" % v for v in out["obj"]]           # R's cat() prints 7 significant digits
+    assert printed == G["printed_objective"]
+
+
+def test_readme_se_head(readme_oracle_fit):
+    se = get_se(readme_oracle_fit)["se_scores"][:6]
+    # reference used irlba(tol=1e-5); the README prints 7 digits
+    np.testing.assert_allclose(se, np.array(G["se_scores_head"]), rtol=0, atol=5e-6)
