@@ -1,0 +1,302 @@
+/*
+ * scgbm.h -- C ABI of libscgbm, the B200-native replacement for the hot path of
+ * phillipnicol/scGBM:  gbm.sc()  (R/fit.R:52-211, pgd_irlba :315-328,
+ * process.results :301-313, gbm.proj.parallel :213-285)  and  get.se()
+ * (R/uncertainty.R:14-35).
+ *
+ * The reference has no native boundary (pure R).  These are the entry points an
+ * R `.Call` shim binds (r-package/src/shim.c) -- plain pointers and sizes, no R,
+ * torch or CUDA types.  Conventions:
+ *   - all matrices are COLUMN-MAJOR (R layout); genes = rows (I), cells = cols (J);
+ *   - the caller owns every buffer it passes; the library owns device memory and
+ *     frees it before returning, also on error;
+ *   - every function returns 0 on success, non-zero on error; the message is
+ *     retrievable with scgbm_last_error() (thread-local);
+ *   - not re-entrant per device; the progress callback fires on the calling thread.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry fails.
+ */
+#ifndef SCGBM_H
+#define SCGBM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCGBM_VERSION 100
+
+/* element type of a count matrix handed to the library */
+enum scgbm_dtype {
+  SCGBM_I32 = 0, /* R integer matrix                    */
+  SCGBM_F64 = 1, /* R double matrix                     */
+  SCGBM_U8  = 2,
+  SCGBM_U16 = 3,
+  SCGBM_F32 = 4
+};
+
+/* device storage format of Y (bytes per stored count = s_Y in the roofline) */
+enum scgbm_storage {
+  SCGBM_STORE_AUTO = 0, /* u16 if max(Y) <= 65535 and integral, else f32 */
+  SCGBM_STORE_U8   = 1,
+  SCGBM_STORE_U16  = 2,
+  SCGBM_STORE_F32  = 3
+};
+
+enum scgbm_status {
+  SCGBM_OK = 0,
+  SCGBM_ERR_INVALID = 1,   /* bad argument; mirrors stop() in R/fit.R:287-299,87 */
+  SCGBM_ERR_CUDA = 2,      /* CUDA / NCCL runtime failure, or no device          */
+  SCGBM_ERR_NUMERIC = 3,   /* e.g. NaN objective followed by NA comparison (Q1), */
+                           /* singular information matrix in get.se              */
+  SCGBM_ERR_NOMEM = 4
+};
+
+/* kernel classes for the built-in CUDA-event profiler (scgbm_profile.ms[k]) */
+enum scgbm_kernel_class {
+  SCGBM_K_PACK = 0,       /* K1 pack + integer stats (R/fit.R:94-96,102-105)      */
+  SCGBM_K_ROWSUM = 1,     /* K3 alpha row sums        (R/fit.R:127-130)           */
+  SCGBM_K_COLSUM = 2,     /* K3 beta col sums         (R/fit.R:133-135)           */
+  SCGBM_K_FUSED = 3,      /* K4 fused likelihood pass (R/fit.R:136-151,321)       */
+  SCGBM_K_PROD_N = 4,     /* K5 R.P   products        (R/fit.R:323)               */
+  SCGBM_K_PROD_T = 5,     /* K5 R^T.Q products        (R/fit.R:323)               */
+  SCGBM_K_SMALL = 6,      /* K6 small dense fp64 (Gram, eig, orth, rotate)        */
+  SCGBM_K_SE = 7,         /* K8 get.se                                            */
+  SCGBM_K_PROJ = 8,       /* K9 projection IRLS                                   */
+  SCGBM_K_COMM = 9,       /* NCCL collectives                                     */
+  SCGBM_K_MISC = 10,
+  SCGBM_K_NCLASS = 11
+};
+
+typedef struct scgbm_profile {
+  double  ms[SCGBM_K_NCLASS];        /* summed CUDA-event time per class            */
+  int64_t launches[SCGBM_K_NCLASS];  /* kernel launches per class                   */
+  double  fused_bytes;               /* algorithmic bytes of ONE fused-pass launch  */
+  double  total_ms;                  /* whole call, device-timed                    */
+  double  h2d_bytes, d2h_bytes;      /* host<->device traffic of the call           */
+  int64_t svd_passes;                /* passes over the materialised residual       */
+  int64_t svd_calls;
+} scgbm_profile;
+
+typedef struct scgbm_comm scgbm_comm; /* opaque: one NCCL rank */
+
+typedef void (*scgbm_progress_cb)(int iter, double objective, void* user);
+
+/* ---- gbm.sc(Y, M, ..., subset = NULL)   R/fit.R:52-211 ------------------------ */
+typedef struct scgbm_fit_args {
+  const void* Y;        /* I x J_local counts, column-major, leading dim ldY        */
+  int32_t  y_dtype;     /* scgbm_dtype                                              */
+  int32_t  y_on_device; /* 0: host pointer; 1: device pointer (stays resident)      */
+  int64_t  I;           /* genes                                                    */
+  int64_t  J;           /* cells held by THIS rank (all cells when comm == NULL)    */
+  int64_t  ldY;         /* >= I                                                     */
+  int32_t  M;           /* latent factors (R/fit.R:53)                              */
+  int32_t  max_iter;    /* R default 100                                            */
+  double   tol;         /* R default 1e-4                                           */
+  int32_t  min_iter;    /* R default 30                                             */
+  int32_t  infer_beta;  /* R default FALSE                                          */
+  const int32_t* batch; /* J 1-based batch codes (as.integer(factor), R/fit.R:90) or NULL */
+  int32_t  nbatch;      /* max(batch) over ALL ranks; 1 when batch == NULL          */
+  int32_t  return_W;    /* fill out->W (I x J doubles)                              */
+  int32_t  time_by_iter;/* fill out->time                                           */
+  /* --- extensions (zero = default) --- */
+  int32_t  y_storage;   /* scgbm_storage                                            */
+  int32_t  device;      /* CUDA ordinal; <0: current device                         */
+  scgbm_comm* comm;     /* NULL: single GPU; else cells are sharded over the ranks  */
+  int32_t  svd_extra;   /* Krylov block = M + svd_extra   (default 12)              */
+  int32_t  svd_depth;   /* max Krylov extensions per cycle (default 3)              */
+  double   svd_tol;     /* Ritz residual estimate to stop at (default 1e-4)         */
+  uint64_t seed;        /* start block of the initial SVD                           */
+  int32_t  profile;     /* 1: per-class CUDA-event timing into out->prof            */
+  int32_t  verbose;
+  scgbm_progress_cb progress; /* called once per accepted iteration (R/fit.R:175)   */
+  void*    progress_user;
+} scgbm_fit_args;
+
+typedef struct scgbm_fit_out {
+  /* caller-allocated, column-major doubles; V/beta/W cover this rank's cells */
+  double* U;      /* I x M   last pgd_irlba left vectors, sign-fixed (R/fit.R:195,304-309) */
+  double* D;      /* M                                                                       */
+  double* V;      /* J x M   sign-fixed                                                      */
+  double* loadings; /* I x M  U BEFORE the sign flip (R/fit.R:196, quirk Q7); may be NULL    */
+  double* scores; /* J x M   V diag(D) (R/fit.R:310); may be NULL                            */
+  double* alpha;  /* I x nbatch                                                              */
+  double* beta;   /* J                                                                       */
+  double* obj;    /* max_iter: accepted objectives (R/fit.R:174)                             */
+  double* time;   /* max_iter or NULL: cumulative seconds (R/fit.R:139-142,203)              */
+  double* W;      /* I x J or NULL (R/fit.R:189-191, unclipped)                              */
+  double* LL;     /* max_iter or NULL: objective of EVERY iteration (diagnostic)             */
+  int8_t* accepted; /* max_iter or NULL: 1 = accepted, 0 = reverted / break (diagnostic)     */
+  /* scalars written by the library */
+  int32_t n_obj;        /* entries of obj                                                    */
+  int32_t n_iter;       /* loop trips, accepted or not                                       */
+  int32_t hit_max_iter; /* R/fit.R:182-185 warning                                           */
+  int32_t y_storage;    /* format actually used                                              */
+  double  max_Y;
+  scgbm_profile prof;
+} scgbm_fit_out;
+
+int scgbm_fit(const scgbm_fit_args* args, scgbm_fit_out* out);
+
+/* ---- get.se(out, EPS)   R/uncertainty.R:14-35 --------------------------------- */
+typedef struct scgbm_se_args {
+  int64_t I, J;         /* J = this rank's cells                                    */
+  int32_t M;
+  const double* U;      /* I x M  (out$U)                                           */
+  const double* scores; /* J x M  (out$scores = V diag(D))                          */
+  const double* W;      /* I x J  (out$W) or NULL -> W = exp(alpha + beta + Xu Xv^T)*/
+  /* used when W == NULL (extension; W of the reverted X, quirk Q6):              */
+  const double* alpha;  /* I x nbatch */
+  const double* beta;   /* J          */
+  const int32_t* batch; /* J or NULL  */
+  int32_t nbatch;
+  const double* Xu;     /* I x Mx left factor of X (already scaled by d) */
+  const double* Xv;     /* J x Mx right factor of X                      */
+  int32_t Mx;
+  double  EPS;          /* R default 0 */
+  int32_t device;
+  scgbm_comm* comm;
+  int32_t profile;
+} scgbm_se_args;
+
+typedef struct scgbm_se_out {
+  double* se_scores;   /* J x M */
+  double* se_loadings; /* I x M */
+  int64_t n_singular;  /* matrices that were not positive definite */
+  scgbm_profile prof;
+} scgbm_se_out;
+
+int scgbm_get_se(const scgbm_se_args* args, scgbm_se_out* out);
+
+/* ---- projection step of gbm.sc(subset = ...)   R/fit.R:229-270 ---------------- */
+typedef struct scgbm_proj_args {
+  const void* Y;        /* I_full x J counts, column-major (all genes)              */
+  int32_t  y_dtype;
+  int32_t  y_on_device;
+  int64_t  I_full, J, ldY;
+  const int64_t* ixs;   /* Ik 0-based gene rows kept by the subsample fit (R/fit.R:225) */
+  int64_t  Ik;
+  int32_t  M;
+  const double* U;      /* Ik x M  loadings of the subsample fit (R/fit.R:229)      */
+  const double* alpha;  /* Ik      offset (R/fit.R:234)                             */
+  double   glm_tol;     /* fastglm default 1e-8 */
+  int32_t  glm_maxit;   /* fastglm default 100  */
+  int32_t  device;
+  int32_t  profile;
+} scgbm_proj_args;
+
+typedef struct scgbm_proj_out {
+  double* beta;       /* J      intercept coefficient (R/fit.R:270)  */
+  double* scores;     /* J x M  (R/fit.R:269)                        */
+  double* se_scores;  /* J x M  (R/fit.R:268)                        */
+  int8_t* fail;       /* J: 1 = GLM failed, row left at zero (R/fit.R:251-261) */
+  int32_t* iters;     /* J or NULL: IRLS iterations used             */
+  scgbm_profile prof;
+} scgbm_proj_out;
+
+int scgbm_project(const scgbm_proj_args* args, scgbm_proj_out* out);
+
+/* ---- synthetic inputs on device (simData recipe, R/simulate.R:24-48) ---------- */
+typedef struct scgbm_sim_args {
+  int64_t I, J, ld;     /* ld >= I: leading dimension of the output               */
+  int64_t j_offset;     /* global index of this shard's first cell (seeding)       */
+  int32_t d;            /* latent factors; 0 -> null model                         */
+  const double* U;      /* I x d (orthonormal) or NULL when d == 0                 */
+  const double* V;      /* J x d rows of this shard                                */
+  const double* D;      /* d                                                       */
+  const double* alpha;  /* I                                                       */
+  const double* beta;   /* J                                                       */
+  double   nb_theta;    /* <= 0: Poisson; > 0: negative binomial (simNullNB)       */
+  uint64_t seed;
+  int32_t  out_dtype;   /* SCGBM_U16 / SCGBM_U8 / SCGBM_F32 / SCGBM_I32            */
+  int32_t  device;
+} scgbm_sim_args;
+
+/* writes counts into the DEVICE buffer `Y_dev` (I x J, leading dim ld); returns the
+ * number of entries that saturated the output type in *n_saturated. */
+int scgbm_sim_counts(const scgbm_sim_args* args, void* Y_dev, int64_t* n_saturated);
+
+/* ---- device memory helpers for callers that keep Y resident ------------------- */
+int scgbm_dev_alloc(void** p, int64_t bytes, int device);
+int scgbm_dev_free(void* p, int device);
+int scgbm_memcpy_d2h(void* dst_host, const void* src_dev, int64_t bytes, int device);
+int scgbm_memcpy_h2d(void* dst_dev, const void* src_host, int64_t bytes, int device);
+int scgbm_host_alloc_pinned(void** p, int64_t bytes);
+int scgbm_host_free_pinned(void* p);
+int scgbm_flush_l2(int device);   /* writes a buffer larger than L2 */
+
+/* ---- multi-GPU: one rank per GPU (NCCL loaded lazily with dlopen) ------------- */
+#define SCGBM_UNIQUE_ID_BYTES 128
+int  scgbm_comm_unique_id(uint8_t id[SCGBM_UNIQUE_ID_BYTES]);
+int  scgbm_comm_init_rank(scgbm_comm** comm, const uint8_t id[SCGBM_UNIQUE_ID_BYTES],
+                          int nranks, int rank, int device);
+int  scgbm_comm_destroy(scgbm_comm* comm);
+int  scgbm_comm_allreduce_f64(scgbm_comm* comm, double* host_buf, int64_t n, int op_max);
+
+/* ---- misc ---------------------------------------------------------------------- */
+const char* scgbm_last_error(void);
+int  scgbm_device_count(void);
+int  scgbm_version(void);
+
+/* ---- diagnostic entry points (kernel-level parity tests and micro-benchmarks) -- */
+/* truncated SVD of G = sum_t coef[t] * A_t diag(d_t) B_t^T + c * R  by the same
+ * warm-started block-Krylov driver the fit uses.  R: I x J fp32 host, column-major. */
+typedef struct scgbm_tsvd_args {
+  int64_t I, J;
+  const float* R;       /* I x J or NULL            */
+  double  c;
+  int32_t nterms;       /* 0..2                     */
+  const double* A[2];   /* I x Mt[t]                */
+  const double* d[2];   /* Mt[t]                    */
+  const double* B[2];   /* J x Mt[t]                */
+  int32_t Mt[2];
+  double  coef[2];
+  int32_t M;
+  int32_t svd_extra, svd_depth;
+  double  svd_tol;
+  const double* V0;     /* J x (M+svd_extra) warm start or NULL */
+  uint64_t seed;
+  int32_t device;
+  int32_t kernel_variant; /* 0 default, 1 force FFMA products, 2 force tcgen05 */
+} scgbm_tsvd_args;
+
+typedef struct scgbm_tsvd_out {
+  double* U;  /* I x M */
+  double* D;  /* M     */
+  double* V;  /* J x M */
+  int32_t passes;
+  double  est;
+} scgbm_tsvd_out;
+
+int scgbm_dbg_tsvd(const scgbm_tsvd_args* args, scgbm_tsvd_out* out);
+
+/* one evaluation of the loop body up to the objective (R/fit.R:127-151) for given
+ * X = Xu Xv^T (optionally clamped to +-8), beta in / alpha,beta out. */
+typedef struct scgbm_eval_args {
+  const void* Y; int32_t y_dtype; int64_t I, J, ldY;
+  int32_t y_storage;
+  const double* Xu; const double* Xv; int32_t Mx; int32_t clamp8;
+  const double* rowscale; /* I or NULL: X0 row scaling s_i   (R/fit.R:117) */
+  const double* colscale; /* J or NULL: X0 col scaling t_j                  */
+  const double* beta_in;  /* J */
+  int32_t infer_beta;
+  int32_t device;
+} scgbm_eval_args;
+
+typedef struct scgbm_eval_out {
+  double* alpha;   /* I */
+  double* beta;    /* J */
+  double* resid;   /* I x J or NULL: Y - min(W, max.Y) as stored on device (fp32 -> double) */
+  double  sum_w, sum_ylogw, max_w, max_Y, LL;
+} scgbm_eval_out;
+
+int scgbm_dbg_eval(const scgbm_eval_args* args, scgbm_eval_out* out);
+
+/* symmetric eigen-decomposition on device (Jacobi): A (n x n, col-major) ->
+ * eigenvalues descending in w, eigenvectors in the columns of A. */
+int scgbm_dbg_eigh(double* A, double* w, int32_t n, int32_t device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCGBM_H */

@@ -1,0 +1,178 @@
+"""Host-side mirror of the reference's R interface for the hot path
+(`gbm.sc`, R/fit.R:52-62; `get.se`, R/uncertainty.R:14) on top of the C ABI.
+
+R is not installed in this image, so this module plays the role the R wrapper in
+`r-package/` plays for R users: same argument names and meaning, same returned
+list (as an ordered dict with R's element order, quirk Q13), same error behaviour
+(`RError` for `stop()`, `warnings.warn` for `warning()`).  All numerics happen in
+libscgbm.so on the GPU; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+import warnings
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _lib as L
+
+
+class RError(L.ScgbmError):
+    """An R `stop()` raised by the reference for the same input."""
+
+
+_NP2DT = {np.dtype(np.int32): L.I32, np.dtype(np.float64): L.F64, np.dtype(np.uint8): L.U8,
+          np.dtype(np.uint16): L.U16, np.dtype(np.float32): L.F32}
+
+
+def _as_counts(Y):
+    """Column-major view acceptable to the C ABI (R matrices are column-major)."""
+    Y = np.asarray(Y)
+    if Y.ndim != 2:
+        raise RError(1, "Y must be a matrix")
+    if Y.dtype not in _NP2DT:
+        if np.issubdtype(Y.dtype, np.integer) or Y.dtype == np.bool_:
+            Y = Y.astype(np.int32)
+        else:
+            Y = Y.astype(np.float64)
+    if not Y.flags.f_contiguous:
+        Y = np.asfortranarray(Y)
+    return Y, _NP2DT[Y.dtype]
+
+
+def _batch_codes(batch, J):
+    """R: `batch` must be a factor (R/fit.R:86-88); here: any 1-D array of labels.
+    Returns 1-based int32 codes in order of first appearance of the SORTED levels
+    (as.integer(factor(x)))."""
+    if batch is None:
+        return None, 1
+    b = np.asarray(batch)
+    if b.shape != (J,):
+        raise RError(1, "Batch must be encoded as factor.")
+    levels, codes = np.unique(b, return_inverse=True)
+    return np.ascontiguousarray(codes.astype(np.int32) + 1), int(len(levels))
+
+
+def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False, return_W=True,
+           batch=None, time_by_iter=False, min_iter=30, *, device=-1, comm=None, y_storage=L.STORE_AUTO,
+           svd_extra=0, svd_depth=0, svd_tol=0.0, seed=0, profile=False, verbose=False, quiet=True,
+           diagnostics=False, y_device_ptr=None, y_device_shape=None, y_device_dtype=None, rng=None):
+    """gbm.sc(Y, M, max.iter, tol, subset, ncores, infer.beta, return.W, batch,
+    time.by.iter, min.iter)   -- R/fit.R:52-62.
+
+    Extensions (keyword only): `device`, `comm` (one NCCL rank per GPU; Y then holds
+    this rank's cells), `y_storage`, `svd_*`, `seed`, `profile`, `diagnostics`
+    (adds `_LL`, `_accepted`, `_n_iter`, `_prof`), `y_device_ptr` (Y already
+    resident in HBM in the library's own layout).
+    """
+    if subset is not None:                                     # R/fit.R:67-73
+        from .projection import gbm_proj_parallel
+        out = gbm_proj_parallel(Y, M, subsample=subset, ncores=ncores, tol=tol, max_iter=max_iter,
+                                device=device, rng=rng, profile=profile, svd_tol=svd_tol, seed=seed)
+        if not quiet:
+            print("For users of newer versions (1.0.1+): the `scores` matrix now contains factor scores.",
+                  file=sys.stderr)
+        return out
+    lib = L.load()
+    if y_device_ptr is not None:
+        I, J = y_device_shape
+        y_ptr, y_dt, on_dev, ldY = C.c_void_p(y_device_ptr), y_device_dtype, 1, ((I + 63) // 64) * 64
+        Yh = None
+    else:
+        Yh, y_dt = _as_counts(Y)
+        I, J = Yh.shape
+        y_ptr, on_dev, ldY = L.ptr(Yh), 0, I
+    if M < 1:
+        raise RError(1, "M must be >= 1")                      # R/fit.R:296-298
+    M = int(M)
+    codes, nbatch = _batch_codes(batch, J)
+    if comm is not None and codes is not None:
+        nbatch = int(comm.allreduce_max_int(nbatch))
+    max_iter = int(max_iter)
+    U = np.zeros((I, M), order="F"); V = np.zeros((J, M), order="F"); D = np.zeros(M)
+    loadings = np.zeros((I, M), order="F"); scores = np.zeros((J, M), order="F")
+    alpha = np.zeros((I, nbatch), order="F"); beta = np.zeros(J)
+    obj = np.zeros(max_iter); LLv = np.zeros(max_iter); acc = np.zeros(max_iter, dtype=np.int8)
+    tvec = np.zeros(max_iter) if time_by_iter else None
+    W = np.zeros((I, J), order="F") if return_W else None
+
+    def _cb(it, objective, _user):
+        if not quiet:
+            print("Iteration: ", it, ". Objective=", "%.7g" % objective)   # R/fit.R:175
+    cb = L.PROGRESS_CB(_cb)
+
+    a = L.FitArgs()
+    a.Y = y_ptr; a.y_dtype = y_dt; a.y_on_device = on_dev; a.I = I; a.J = J; a.ldY = ldY
+    a.M = M; a.max_iter = max_iter; a.tol = float(tol); a.min_iter = int(min_iter)
+    a.infer_beta = int(bool(infer_beta)); a.batch = L.ptr(codes); a.nbatch = nbatch
+    a.return_W = int(bool(return_W)); a.time_by_iter = int(bool(time_by_iter))
+    a.y_storage = int(y_storage); a.device = int(device)
+    a.comm = comm.handle if comm is not None else None
+    a.svd_extra = int(svd_extra); a.svd_depth = int(svd_depth); a.svd_tol = float(svd_tol)
+    a.seed = int(seed); a.profile = int(bool(profile)); a.verbose = int(bool(verbose))
+    a.progress = cb; a.progress_user = None
+    o = L.FitOut()
+    o.U = L.ptr(U); o.D = L.ptr(D); o.V = L.ptr(V); o.loadings = L.ptr(loadings); o.scores = L.ptr(scores)
+    o.alpha = L.ptr(alpha); o.beta = L.ptr(beta); o.obj = L.ptr(obj); o.time = L.ptr(tvec)
+    o.W = L.ptr(W); o.LL = L.ptr(LLv); o.accepted = L.ptr(acc)
+    st = lib.scgbm_fit(C.byref(a), C.byref(o))
+    if st == 1:
+        raise RError(st, (lib.scgbm_last_error() or b"").decode())
+    L.check(st)
+    if o.hit_max_iter:                                          # R/fit.R:182-185
+        warnings.warn("Maximum number of iterations reached (increase max.iter).\n"
+                      "              Possible non-convergence.")
+    out = OrderedDict()                                         # element order: quirk Q13
+    if return_W:
+        out["W"] = W
+    out["V"] = V; out["D"] = D; out["U"] = U; out["loadings"] = loadings
+    out["alpha"] = alpha; out["beta"] = beta; out["M"] = M
+    if return_W:                                                # Q9: I, J only exist with W
+        out["I"] = I; out["J"] = J
+    out["obj"] = obj[: o.n_obj].copy()
+    if time_by_iter:
+        out["time"] = tvec[: o.n_iter].copy()
+    out["scores"] = scores
+    if not quiet:
+        print("For users of newer versions (1.0.1+): the `scores` matrix now contains factor scores, "
+              "the `V` matrix is UNSCALED scores.", file=sys.stderr)   # R/fit.R:209
+    if diagnostics or profile:
+        out["_LL"] = LLv[: o.n_iter].copy()
+        out["_accepted"] = acc[: o.n_iter].astype(bool)
+        out["_n_iter"] = int(o.n_iter)
+        out["_hit_max_iter"] = bool(o.hit_max_iter)
+        out["_y_storage"] = int(o.y_storage)
+        out["_max_Y"] = float(o.max_Y)
+        out["_prof"] = o.prof.as_dict()
+    return out
+
+
+def get_se(out, EPS=0.0, *, device=-1, profile=False):
+    """get.se(out, EPS)  -- R/uncertainty.R:14-35.  Needs out['W'] like the reference
+    (quirk Q9)."""
+    lib = L.load()
+    if "W" not in out or out["W"] is None:
+        raise RError(1, "get.se needs out$W: fit with return.W = TRUE (R/uncertainty.R:18)")
+    U = np.asfortranarray(out["U"], dtype=np.float64)
+    S = np.asfortranarray(out["scores"], dtype=np.float64)
+    W = np.asfortranarray(out["W"], dtype=np.float64)
+    I, J = W.shape
+    M = len(out["D"])
+    se_s = np.zeros((J, M), order="F"); se_l = np.zeros((I, M), order="F")
+    a = L.SeArgs()
+    a.I = I; a.J = J; a.M = M; a.U = L.ptr(U); a.scores = L.ptr(S); a.W = L.ptr(W)
+    a.EPS = float(EPS); a.device = int(device); a.nbatch = 1; a.profile = int(bool(profile))
+    o = L.SeOut()
+    o.se_scores = L.ptr(se_s); o.se_loadings = L.ptr(se_l)
+    st = lib.scgbm_get_se(C.byref(a), C.byref(o))
+    if st in (1, 3):
+        raise RError(st, (lib.scgbm_last_error() or b"").decode())
+    L.check(st)
+    res = OrderedDict(out)
+    res["se_scores"] = se_s                                     # R/uncertainty.R:26
+    res["se_loadings"] = se_l                                   # R/uncertainty.R:33
+    if profile:
+        res["_prof_se"] = o.prof.as_dict()
+    return res

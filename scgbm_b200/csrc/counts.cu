@@ -1,0 +1,427 @@
+// counts.cu -- K1: pack the count matrix into its device format and compute the exact
+// integer statistics the fit needs (max(Y), colSums, per-batch rowSums: R/fit.R:94-96,
+// 102-105) while validating the input (R/fit.R:287-299).  Also the on-device
+// simData-style generator (R/simulate.R:24-48,60-65) used for benchmark inputs.
+#include "counts.cuh"
+
+namespace scgbm {
+
+struct PackStats {
+  unsigned long long max_bits;  // bit pattern of the max as a non-negative double
+  int flags;                    // 1: negative, 2: NaN, 4: non-integral, 8: does not fit Tout
+};
+
+template <typename T> struct OutLimit;
+template <> struct OutLimit<uint8_t> { static constexpr double max = 255.0; static constexpr bool integral = true; };
+template <> struct OutLimit<uint16_t> { static constexpr double max = 65535.0; static constexpr bool integral = true; };
+template <> struct OutLimit<float> { static constexpr double max = 3.0e38; static constexpr bool integral = false; };
+
+constexpr int PK_ROWS = 256, PK_COLS = 16;
+
+// in: rows x jc (ld_in); out: ld_out x jc, rows >= n_rows are written as zero.
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(PK_ROWS)
+pack_stats_kernel(const Tin* __restrict__ in, int64_t ld_in, const int64_t* __restrict__ rowmap,
+                  int64_t n_rows, int64_t ld_out, int64_t jc, Tout* __restrict__ out,
+                  const int32_t* __restrict__ batch, double* __restrict__ colsum,
+                  double* __restrict__ rowsum, PackStats* __restrict__ st, int write_out) {
+  __shared__ double s_col[PK_COLS][PK_ROWS / 32];
+  const int64_t i = (int64_t)blockIdx.x * PK_ROWS + threadIdx.x;
+  const int64_t j0 = (int64_t)blockIdx.y * PK_COLS;
+  const bool active = i < n_rows;
+  const int64_t src_row = active ? (rowmap ? rowmap[i] : i) : 0;
+  double racc = 0.0;
+  int rb = -1;
+  double vmax = 0.0;
+  int flags = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int jj = 0; jj < PK_COLS; ++jj) {
+    const int64_t j = j0 + jj;
+    double v = 0.0;
+    if (j < jc && active) {
+      v = (double)in[j * ld_in + src_row];
+      if (v != v) { flags |= 2; v = 0.0; }
+      if (v < 0.0) flags |= 1;
+      if (OutLimit<Tout>::integral && v != floor(v)) flags |= 4;
+      if (v > OutLimit<Tout>::max) flags |= 8;
+      vmax = fmax(vmax, v);
+      const int b = batch ? batch[j] : 0;
+      if (b != rb) {
+        if (rb >= 0 && racc != 0.0) atomicAdd(&rowsum[(int64_t)rb * ld_out + i], racc);
+        rb = b; racc = 0.0;
+      }
+      racc += v;
+    }
+    if (j < jc && write_out && i < ld_out) out[j * ld_out + i] = (Tout)v;
+    const double cs = warp_sum(v);
+    if (lane == 0) s_col[jj][warp] = cs;
+  }
+  if (rb >= 0 && racc != 0.0) atomicAdd(&rowsum[(int64_t)rb * ld_out + i], racc);
+  __syncthreads();
+  if (threadIdx.x < PK_COLS) {
+    const int64_t j = j0 + threadIdx.x;
+    if (j < jc) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < PK_ROWS / 32; ++w) s += s_col[threadIdx.x][w];
+      if (s != 0.0) atomicAdd(&colsum[j], s);   // integer-valued sums: order-independent
+    }
+  }
+  vmax = warp_max(vmax);
+  flags |= __shfl_xor_sync(0xffffffffu, flags, 16);
+  flags |= __shfl_xor_sync(0xffffffffu, flags, 8);
+  flags |= __shfl_xor_sync(0xffffffffu, flags, 4);
+  flags |= __shfl_xor_sync(0xffffffffu, flags, 2);
+  flags |= __shfl_xor_sync(0xffffffffu, flags, 1);
+  if (lane == 0) {
+    if (vmax > 0.0) atomicMax(&st->max_bits, (unsigned long long)__double_as_longlong(vmax));
+    if (flags) atomicOr(&st->flags, flags);
+  }
+}
+
+template <typename Tin, typename Tout>
+static void launch_pack(Ctx& ctx, cudaStream_t s, const void* in, int64_t ld_in, const int64_t* rowmap,
+                        int64_t n_rows, int64_t ld_out, int64_t jc, void* out, const int32_t* batch,
+                        double* colsum, double* rowsum, PackStats* st, int write_out) {
+  dim3 grid((unsigned)ceil_div(ld_out, PK_ROWS), (unsigned)ceil_div(jc, PK_COLS));
+  pack_stats_kernel<Tin, Tout><<<grid, PK_ROWS, 0, s>>>((const Tin*)in, ld_in, rowmap, n_rows, ld_out, jc,
+                                                        (Tout*)out, batch, colsum, rowsum, st, write_out);
+  SCGBM_LAUNCH_CHECK();
+}
+
+template <typename Tout>
+static void launch_pack_in(Ctx& ctx, cudaStream_t s, int y_dtype, const void* in, int64_t ld_in,
+                           const int64_t* rowmap, int64_t n_rows, int64_t ld_out, int64_t jc, void* out,
+                           const int32_t* batch, double* colsum, double* rowsum, PackStats* st,
+                           int write_out) {
+  switch (y_dtype) {
+    case SCGBM_I32: launch_pack<int32_t, Tout>(ctx, s, in, ld_in, rowmap, n_rows, ld_out, jc, out, batch, colsum, rowsum, st, write_out); break;
+    case SCGBM_F64: launch_pack<double, Tout>(ctx, s, in, ld_in, rowmap, n_rows, ld_out, jc, out, batch, colsum, rowsum, st, write_out); break;
+    case SCGBM_U8: launch_pack<uint8_t, Tout>(ctx, s, in, ld_in, rowmap, n_rows, ld_out, jc, out, batch, colsum, rowsum, st, write_out); break;
+    case SCGBM_U16: launch_pack<uint16_t, Tout>(ctx, s, in, ld_in, rowmap, n_rows, ld_out, jc, out, batch, colsum, rowsum, st, write_out); break;
+    case SCGBM_F32: launch_pack<float, Tout>(ctx, s, in, ld_in, rowmap, n_rows, ld_out, jc, out, batch, colsum, rowsum, st, write_out); break;
+    default: throw Error(SCGBM_ERR_INVALID, "unknown y_dtype");
+  }
+}
+
+static int dtype_bytes(int y_dtype) {
+  switch (y_dtype) {
+    case SCGBM_I32: return 4; case SCGBM_F64: return 8; case SCGBM_U8: return 1;
+    case SCGBM_U16: return 2; case SCGBM_F32: return 4;
+  }
+  throw Error(SCGBM_ERR_INVALID, "unknown y_dtype");
+}
+
+static void pack_dispatch(Ctx& ctx, cudaStream_t s, int storage, int y_dtype, const void* in, int64_t ld_in,
+                          const int64_t* rowmap, int64_t n_rows, int64_t ld_out, int64_t jc, void* out,
+                          const int32_t* batch, double* colsum, double* rowsum, PackStats* st, int write_out) {
+  switch (storage) {
+    case SCGBM_STORE_U8: launch_pack_in<uint8_t>(ctx, s, y_dtype, in, ld_in, rowmap, n_rows, ld_out, jc, out, batch, colsum, rowsum, st, write_out); break;
+    case SCGBM_STORE_U16: launch_pack_in<uint16_t>(ctx, s, y_dtype, in, ld_in, rowmap, n_rows, ld_out, jc, out, batch, colsum, rowsum, st, write_out); break;
+    case SCGBM_STORE_F32: launch_pack_in<float>(ctx, s, y_dtype, in, ld_in, rowmap, n_rows, ld_out, jc, out, batch, colsum, rowsum, st, write_out); break;
+    default: throw Error(SCGBM_ERR_INVALID, "unknown storage");
+  }
+}
+
+static void load_impl(Ctx& ctx, const void* Y, int y_dtype, int y_on_device, int64_t I_src, int64_t J,
+                      int64_t ldY, const int64_t* rowmap_host, int64_t n_rows, const int32_t* batch_host,
+                      int nbatch, int storage_req, Counts& c) {
+  SCGBM_REQUIRE(Y != nullptr, "Y is NULL");
+  SCGBM_REQUIRE(n_rows >= 1 && J >= 1, "Y must have at least one row and one column");
+  SCGBM_REQUIRE(ldY >= I_src, "ldY < I");
+  SCGBM_REQUIRE(nbatch >= 1, "nbatch < 1");
+  c.I = n_rows; c.J = J; c.ld = round_up(n_rows, kRowPad); c.nbatch = nbatch;
+  c.colsum.alloc(J);
+  c.rowsum.alloc(c.ld * nbatch);
+  DevBuf<int64_t> rowmap;
+  if (rowmap_host) {
+    rowmap.alloc(n_rows);
+    SCGBM_CUDA(cudaMemcpyAsync(rowmap.get(), rowmap_host, n_rows * sizeof(int64_t), cudaMemcpyHostToDevice, ctx.stream));
+  }
+  if (batch_host && nbatch > 1) {
+    std::vector<int32_t> b0(J);
+    for (int64_t j = 0; j < J; ++j) {
+      SCGBM_REQUIRE(batch_host[j] >= 1 && batch_host[j] <= nbatch, "batch codes must be in 1..nbatch");
+      b0[j] = batch_host[j] - 1;
+    }
+    c.batch.alloc(J);
+    SCGBM_CUDA(cudaMemcpyAsync(c.batch.get(), b0.data(), J * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
+    SCGBM_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+  DevBuf<PackStats> st(1);
+  const int eb = dtype_bytes(y_dtype);
+
+  int storage = storage_req == SCGBM_STORE_AUTO ? SCGBM_STORE_U16 : storage_req;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    c.storage = storage;
+    // alias a resident device matrix that already has the native layout
+    const bool native = y_on_device && !rowmap_host && ldY == c.ld &&
+                        ((storage == SCGBM_STORE_U8 && y_dtype == SCGBM_U8) ||
+                         (storage == SCGBM_STORE_U16 && y_dtype == SCGBM_U16) ||
+                         (storage == SCGBM_STORE_F32 && y_dtype == SCGBM_F32));
+    if (native) {
+      c.owned.release();
+      c.data = const_cast<void*>(Y);
+    } else {
+      c.owned.alloc(c.ld * J * c.elem_bytes());
+      c.data = c.owned.get();
+    }
+    c.colsum.zero(ctx.stream);
+    c.rowsum.zero(ctx.stream);
+    st.zero(ctx.stream);
+    if (y_on_device) {
+      ProfScope ps(ctx.prof, SCGBM_K_PACK, 1);
+      pack_dispatch(ctx, ctx.stream, storage, y_dtype, Y, ldY, rowmap.get(), n_rows, c.ld, J, c.data,
+                    c.batch.get(), c.colsum.get(), c.rowsum.get(), st.get(), native ? 0 : 1);
+    } else {
+      // chunked H2D (copy stream) overlapped with packing (compute stream)
+      int64_t cols_per_chunk = std::max<int64_t>(1, (int64_t)(256ll << 20) / (ldY * eb));
+      cols_per_chunk = std::min(cols_per_chunk, J);
+      DevBuf<uint8_t> raw[2];
+      raw[0].alloc(cols_per_chunk * ldY * eb);
+      if (cols_per_chunk < J) raw[1].alloc(cols_per_chunk * ldY * eb);
+      cudaStream_t cs;
+      SCGBM_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      cudaEvent_t copied[2], packed[2];
+      for (int k = 0; k < 2; ++k) {
+        SCGBM_CUDA(cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming));
+        SCGBM_CUDA(cudaEventCreateWithFlags(&packed[k], cudaEventDisableTiming));
+      }
+      try {
+        SCGBM_CUDA(cudaStreamSynchronize(ctx.stream));
+        int k = 0;
+        int64_t nchunk = 0;
+        for (int64_t j0 = 0; j0 < J; j0 += cols_per_chunk, k ^= 1, ++nchunk) {
+          const int64_t jc = std::min(cols_per_chunk, J - j0);
+          if (nchunk >= 2) SCGBM_CUDA(cudaStreamWaitEvent(cs, packed[k], 0));
+          const uint8_t* src = (const uint8_t*)Y + (size_t)j0 * ldY * eb;
+          // last column may be shorter than ldY in the caller's allocation
+          const size_t bytes = ((size_t)(jc - 1) * ldY + I_src) * eb;
+          SCGBM_CUDA(cudaMemcpyAsync(raw[k].get(), src, bytes, cudaMemcpyHostToDevice, cs));
+          ctx.prof.h2d_bytes += (double)bytes;
+          SCGBM_CUDA(cudaEventRecord(copied[k], cs));
+          SCGBM_CUDA(cudaStreamWaitEvent(ctx.stream, copied[k], 0));
+          {
+            ProfScope ps(ctx.prof, SCGBM_K_PACK, 1);
+            pack_dispatch(ctx, ctx.stream, storage, y_dtype, raw[k].get(), ldY, rowmap.get(), n_rows, c.ld, jc,
+                          (uint8_t*)c.data + (size_t)j0 * c.ld * c.elem_bytes(),
+                          c.batch.get() ? c.batch.get() + j0 : nullptr, c.colsum.get() + j0,
+                          c.rowsum.get(), st.get(), 1);
+          }
+          SCGBM_CUDA(cudaEventRecord(packed[k], ctx.stream));
+        }
+        SCGBM_CUDA(cudaStreamSynchronize(ctx.stream));
+      } catch (...) {
+        cudaStreamSynchronize(cs); cudaStreamDestroy(cs);
+        for (int k = 0; k < 2; ++k) { cudaEventDestroy(copied[k]); cudaEventDestroy(packed[k]); }
+        throw;
+      }
+      cudaStreamSynchronize(cs); cudaStreamDestroy(cs);
+      for (int k = 0; k < 2; ++k) { cudaEventDestroy(copied[k]); cudaEventDestroy(packed[k]); }
+    }
+    PackStats h;
+    SCGBM_CUDA(cudaMemcpyAsync(&h, st.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
+    SCGBM_CUDA(cudaStreamSynchronize(ctx.stream));
+    if (h.flags & 2) throw Error(SCGBM_ERR_INVALID, "Count matrix Y cannot contain NA values.");
+    if (h.flags & 1) throw Error(SCGBM_ERR_INVALID, "Count matrix Y cannot contain negative values.");
+    if (h.flags & (4 | 8)) {
+      if (storage_req == SCGBM_STORE_AUTO && storage != SCGBM_STORE_F32) { storage = SCGBM_STORE_F32; continue; }
+      throw Error(SCGBM_ERR_INVALID, "Y does not fit the requested device storage format");
+    }
+    long long bits = (long long)h.max_bits;
+    double mx;
+    memcpy(&mx, &bits, sizeof(mx));
+    c.maxY = mx;
+    return;
+  }
+}
+
+void load_counts(Ctx& ctx, const void* Y, int y_dtype, int y_on_device, int64_t I, int64_t J, int64_t ldY,
+                 const int32_t* batch_host, int nbatch, int storage_req, Counts& c) {
+  load_impl(ctx, Y, y_dtype, y_on_device, I, J, ldY, nullptr, I, batch_host, nbatch, storage_req, c);
+}
+
+void load_counts_rows(Ctx& ctx, const void* Y, int y_dtype, int y_on_device, int64_t I_full, int64_t J,
+                      int64_t ldY, const int64_t* ixs_host, int64_t Ik, Counts& c) {
+  for (int64_t r = 0; r < Ik; ++r)
+    SCGBM_REQUIRE(ixs_host[r] >= 0 && ixs_host[r] < I_full, "ixs out of range");
+  load_impl(ctx, Y, y_dtype, y_on_device, I_full, J, ldY, ixs_host, Ik, nullptr, 1, SCGBM_STORE_AUTO, c);
+}
+
+// ---------------------------------------------------------------------------------
+// on-device generator: Y ~ Poisson / NB(exp(alpha_i + beta_j + (U D V^T)_ij))
+// counter-based Philox4x32-10 keyed by (seed, element index) so shards are
+// reproducible independently of the launch geometry.
+// ---------------------------------------------------------------------------------
+struct Philox {
+  uint32_t c[4], k[2], out[4];
+  int have;
+  __device__ Philox(uint64_t seed, uint64_t idx) {
+    c[0] = (uint32_t)idx; c[1] = (uint32_t)(idx >> 32); c[2] = 0; c[3] = 0x5C6B0000u;
+    k[0] = (uint32_t)seed; k[1] = (uint32_t)(seed >> 32);
+    have = 0;
+  }
+  __device__ void round_fn(uint32_t* ctr, const uint32_t* key) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr[0]), lo0 = 0xD2511F53u * ctr[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr[2]), lo1 = 0xCD9E8D57u * ctr[2];
+    const uint32_t n0 = hi1 ^ ctr[1] ^ key[0], n1 = lo1, n2 = hi0 ^ ctr[3] ^ key[1], n3 = lo0;
+    ctr[0] = n0; ctr[1] = n1; ctr[2] = n2; ctr[3] = n3;
+  }
+  __device__ void refill() {
+    uint32_t ctr[4] = {c[0], c[1], c[2], c[3]};
+    uint32_t key[2] = {k[0], k[1]};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      round_fn(ctr, key);
+      key[0] += 0x9E3779B9u; key[1] += 0xBB67AE85u;
+    }
+    out[0] = ctr[0]; out[1] = ctr[1]; out[2] = ctr[2]; out[3] = ctr[3];
+    c[2] += 1;
+    have = 4;
+  }
+  __device__ uint32_t next() {
+    if (have == 0) refill();
+    return out[--have];
+  }
+  __device__ double uniform() {  // (0,1), 53-bit
+    const uint64_t a = next() >> 5, b = next() >> 6;
+    return ((double)a * 67108864.0 + (double)b + 0.5) * (1.0 / 9007199254740992.0);
+  }
+  __device__ double normal() {
+    const double u1 = uniform(), u2 = uniform();
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+  }
+  __device__ double gamma(double shape) {  // Marsaglia-Tsang
+    double boost = 1.0;
+    if (shape < 1.0) { boost = pow(uniform(), 1.0 / shape); shape += 1.0; }
+    const double d = shape - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * d);
+    for (int it = 0; it < 1000; ++it) {
+      double x = normal(), v = 1.0 + cc * x;
+      if (v <= 0.0) continue;
+      v = v * v * v;
+      const double u = uniform();
+      if (u < 1.0 - 0.0331 * x * x * x * x) return boost * d * v;
+      if (log(u) < 0.5 * x * x + d * (1.0 - v + log(v))) return boost * d * v;
+    }
+    return boost * d;
+  }
+  __device__ double poisson(double lam) {
+    if (!(lam > 0.0)) return 0.0;
+    if (lam < 12.0) {   // inversion by sequential search
+      const double u = uniform();
+      double p = exp(-lam), q = p;
+      int k = 0;
+      while (u > q && k < 200) { ++k; p *= lam / k; q += p; }
+      return (double)k;
+    }
+    // PTRS (Hoermann 1993)
+    const double slam = sqrt(lam), loglam = log(lam);
+    const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+    const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (int it = 0; it < 1000; ++it) {
+      const double U = uniform() - 0.5, V = uniform();
+      const double us = 0.5 - fabs(U);
+      const double k = floor((2.0 * a / us + b) * U + lam + 0.43);
+      if (us >= 0.07 && V <= vr) return k;
+      if (k < 0.0 || (us < 0.013 && V > us)) continue;
+      if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -lam + k * loglam - lgamma(k + 1.0)) return k;
+    }
+    return floor(lam);
+  }
+};
+
+template <typename Tout> struct SimLimit;
+template <> struct SimLimit<uint8_t> { static constexpr double max = 255.0; };
+template <> struct SimLimit<uint16_t> { static constexpr double max = 65535.0; };
+template <> struct SimLimit<float> { static constexpr double max = 16777216.0; };
+template <> struct SimLimit<int32_t> { static constexpr double max = 2147483647.0; };
+
+template <typename Tout>
+__global__ void __launch_bounds__(256)
+sim_counts_kernel(int64_t I, int64_t J, int64_t ld, int64_t j_offset, int d, const float* __restrict__ Ud,
+                  const float* __restrict__ V, const float* __restrict__ alpha, const float* __restrict__ beta,
+                  double nb_theta, uint64_t seed, Tout* __restrict__ Y, unsigned long long* __restrict__ n_sat) {
+  extern __shared__ float s_v[];   // d floats: V row of this column
+  const int64_t j = blockIdx.y;
+  for (int m = threadIdx.x; m < d; m += blockDim.x) s_v[m] = V[(int64_t)m * J + j];
+  __syncthreads();
+  const float bj = beta[j];
+  unsigned long long sat = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ld; i += (int64_t)gridDim.x * blockDim.x) {
+    Tout outv = (Tout)0;
+    if (i < I) {
+      float x = alpha[i] + bj;
+      for (int m = 0; m < d; ++m) x = fmaf(Ud[(int64_t)m * I + i], s_v[m], x);
+      double lam = exp((double)x);
+      Philox rng(seed, (uint64_t)(j_offset + j) * (uint64_t)I + (uint64_t)i);
+      if (nb_theta > 0.0) lam = rng.gamma(nb_theta) * (lam / nb_theta);
+      double y = rng.poisson(lam);
+      if (y > SimLimit<Tout>::max) { y = SimLimit<Tout>::max; ++sat; }
+      outv = (Tout)y;
+    }
+    Y[j * ld + i] = outv;
+  }
+  if (sat) atomicAdd(n_sat, sat);
+}
+
+__global__ void f64_to_f32_scaled(int64_t n, int q, const double* __restrict__ src, int64_t lds,
+                                  const double* __restrict__ colscale, float* __restrict__ dst, int64_t ldd) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * q) return;
+  const int64_t r = idx % n;
+  const int c = (int)(idx / n);
+  dst[(int64_t)c * ldd + r] = (float)(src[(int64_t)c * lds + r] * (colscale ? colscale[c] : 1.0));
+}
+
+void sim_counts(const scgbm_sim_args* a, void* Y_dev, int64_t* n_saturated) {
+  SCGBM_REQUIRE(a->I >= 1 && a->J >= 1 && a->ld >= a->I, "sim: bad shape");
+  SCGBM_REQUIRE(a->d >= 0 && a->d <= 1024, "sim: bad d");
+  SCGBM_REQUIRE(a->alpha && a->beta, "sim: alpha/beta required");
+  Ctx ctx(a->device, nullptr);
+  const int64_t I = a->I, J = a->J;
+  const int d = a->d;
+  DevBuf<double> tmp(std::max<int64_t>(std::max(I, J) * std::max(d, 1), 1)), Dd(std::max(d, 1));
+  DevBuf<float> Ud(std::max<int64_t>(I * d, 1)), Vf(std::max<int64_t>(J * d, 1)), al(I), be(J);
+  auto conv = [&](const double* host, int64_t n, int q, const double* colscale_dev, float* dst) {
+    SCGBM_CUDA(cudaMemcpyAsync(tmp.get(), host, n * q * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+    f64_to_f32_scaled<<<(unsigned)ceil_div(n * q, 256), 256, 0, ctx.stream>>>(n, q, tmp.get(), n, colscale_dev, dst, n);
+    SCGBM_LAUNCH_CHECK();
+  };
+  if (d > 0) {
+    SCGBM_REQUIRE(a->U && a->V && a->D, "sim: U, V, D required when d > 0");
+    SCGBM_CUDA(cudaMemcpyAsync(Dd.get(), a->D, d * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+    conv(a->U, I, d, Dd.get(), Ud.get());
+    conv(a->V, J, d, nullptr, Vf.get());
+  }
+  conv(a->alpha, I, 1, nullptr, al.get());
+  conv(a->beta, J, 1, nullptr, be.get());
+  DevBuf<unsigned long long> nsat(1);
+  nsat.zero(ctx.stream);
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(a->ld, 256), 64), (unsigned)J);
+  SCGBM_REQUIRE(J <= 2147483647ll, "sim: J too large for one launch");
+  // blockIdx.y is limited to 65535: loop over column slabs
+  const int64_t slab = 65535;
+  for (int64_t j0 = 0; j0 < J; j0 += slab) {
+    const int64_t jc = std::min(slab, J - j0);
+    dim3 g(grid.x, (unsigned)jc);
+    const size_t sm = std::max(d, 1) * sizeof(float);
+#define SIM_LAUNCH(T)                                                                              \
+    sim_counts_kernel<T><<<g, 256, sm, ctx.stream>>>(I, J, a->ld, a->j_offset + j0, d, Ud.get(),    \
+        Vf.get() + j0, al.get(), be.get() + j0, a->nb_theta, a->seed, (T*)Y_dev + j0 * a->ld, nsat.get())
+    switch (a->out_dtype) {
+      case SCGBM_U8: SIM_LAUNCH(uint8_t); break;
+      case SCGBM_U16: SIM_LAUNCH(uint16_t); break;
+      case SCGBM_F32: SIM_LAUNCH(float); break;
+      case SCGBM_I32: SIM_LAUNCH(int32_t); break;
+      default: throw Error(SCGBM_ERR_INVALID, "sim: unsupported out_dtype");
+    }
+#undef SIM_LAUNCH
+    SCGBM_LAUNCH_CHECK();
+  }
+  unsigned long long h = 0;
+  SCGBM_CUDA(cudaMemcpyAsync(&h, nsat.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  if (n_saturated) *n_saturated = (int64_t)h;
+}
+
+}  // namespace scgbm

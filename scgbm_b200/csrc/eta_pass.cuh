@@ -1,0 +1,49 @@
+// eta_pass.cuh -- K3/K4: the dense "evaluate eta" passes of the loop body
+// (R/fit.R:127-151, :321).  X is never materialised: it is rebuilt per tile from
+// shared-memory-staged factor tiles.
+#pragma once
+#include "common.cuh"
+#include "counts.cuh"
+
+namespace scgbm {
+
+// X_ij = clamp?( rowscale?[i, b(j)] * sum_m A[i,m] B[j,m] )
+struct XDesc {
+  const float* A = nullptr;   // ldI x M (col-major), d (and single-batch row scale) folded in
+  const float* B = nullptr;   // ldJ x M (col-major), column scale folded in
+  int M = 0;                  // 0 -> X == 0
+  int clamp = 0;              // clamp to [-8, 8]   (R/fit.R:119-120)
+  const float* rowscale = nullptr;  // ldI x nbatch or null (multi-batch X0 only)
+};
+
+struct PassGeom {
+  int64_t I, J, ldI, ldJ;
+  int nbatch;
+  const int32_t* batch;  // J zero-based or null
+};
+
+struct EtaWs {
+  DevBuf<double> row_part;   // [chunks][nbatch][ldI]
+  DevBuf<double> scal_part;  // [ctas][4]
+  DevBuf<double> scal;       // [4]: sum_w, sum_ylogw, max_w, spare
+};
+
+// S[i,k] = sum_{j in batch k} g_j * exp(X_ij)      (R/fit.R:129)   -> S (ldI x nbatch, fp64)
+void pass_rowsum(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* g_col, double* S);
+
+// C[j] = sum_i f_{i,b(j)} * exp(X_ij)               (R/fit.R:134)   -> C (J, fp64)
+void pass_colsum(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* f_row, double* C);
+
+// W = min(f_i g_j exp(X_ij), max.Y); resid = Y - W (fp32, ldI x J); scalars:
+// out[0] = sum W, out[1] = sum_{Y != 0} Y log W, out[2] = max W    (R/fit.R:136-151,321)
+void pass_fused(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const Counts& y,
+                const float* f_row, const float* g_col, const float* la_row, const float* lb_col,
+                float maxY, float* resid, double* out3);
+
+// resid += coef * X_ij   (iterations 1-2: the clamped, non-low-rank X0 terms of G)
+void pass_addx(Ctx& ctx, const PassGeom& g, const XDesc& x, float coef, float* resid);
+
+// algorithmic bytes of one fused-pass launch (SURVEY 8d / BASELINE.md section 4)
+double fused_pass_bytes(const PassGeom& g, const XDesc& x, int y_elem_bytes);
+
+}  // namespace scgbm

@@ -1,0 +1,678 @@
+// fit.cu -- K7: host control of gbm.sc's full-data fit (R/fit.R:76-211) over device
+// state.  X is never an I x J matrix: it is one of three factor slots; the only I x J
+// device objects are Y (compact counts) and the fp32 residual R.
+#include <chrono>
+#include "common.cuh"
+#include "counts.cuh"
+#include "eta_pass.cuh"
+#include "tsvd.cuh"
+
+namespace scgbm {
+
+enum { XK_ZERO = 0, XK_LOWRANK = 1, XK_X0 = 2 };
+
+struct Factor {
+  int kind = XK_ZERO;
+  int M = 0;
+  DevBuf<double> U, d, V;      // ldI x M, M, ldJ x M   (orthonormal factors from the SVD)
+  DevBuf<float> A32, B32;      // fp32 tiles for the eta passes: A32 = U d (* row scale), B32 = V (* col scale)
+  void alloc(int64_t ldI, int64_t ldJ, int M_) {
+    M = M_;
+    U.alloc(ldI * M); d.alloc(M); V.alloc(ldJ * M); A32.alloc(ldI * M); B32.alloc(ldJ * M);
+  }
+};
+
+// ---- small elementwise kernels ----------------------------------------------------
+__global__ void log_kernel(int64_t n, const double* __restrict__ x, double* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = log(x[i]);
+}
+
+// single CTA: alpha = logrs - log(S) on the I real rows of each batch column, then
+// recentre:  shift = mean(alpha); alpha -= shift   (R/fit.R:127-132 and :106-110)
+__global__ void __launch_bounds__(1024)
+alpha_update_kernel(int64_t I, int64_t ldI, int nbatch, const double* __restrict__ logrs,
+                    const double* __restrict__ S, const double* __restrict__ logtot, double* __restrict__ alpha,
+                    double* __restrict__ shift) {
+  __shared__ double red[1024];
+  double s = 0.0;
+  for (int64_t idx = threadIdx.x; idx < I * nbatch; idx += 1024) {
+    const int64_t i = idx % I;
+    const int k = (int)(idx / I);
+    const double a = logrs[k * ldI + i] - (S ? log(S[k * ldI + i]) : logtot[k]);
+    alpha[k * ldI + i] = a;
+    s += a;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int st = 512; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  const double mean = red[0] / (double)(I * nbatch);
+  for (int64_t idx = threadIdx.x; idx < I * nbatch; idx += 1024) {
+    const int64_t i = idx % I;
+    const int k = (int)(idx / I);
+    alpha[k * ldI + i] -= mean;
+  }
+  if (threadIdx.x == 0) shift[0] = mean;
+}
+
+__global__ void beta_shift_kernel(int64_t J, double* __restrict__ beta, const double* __restrict__ shift) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < J) beta[j] += shift[0];
+}
+
+// beta_j = logcs_j - log(C_j)    (R/fit.R:134)
+__global__ void beta_infer_kernel(int64_t J, const double* __restrict__ logcs, const double* __restrict__ C,
+                                  double* __restrict__ beta) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < J) beta[j] = logcs[j] - log(C[j]);
+}
+
+// fp32 staging: e[i] = exp(scale * x[i]) and l[i] = x[i]; rows >= n_real get 0
+__global__ void exp_stage_kernel(int64_t n_real, int64_t ld, int ncol, const double* __restrict__ x, double scale,
+                                 float* __restrict__ e, float* __restrict__ l) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ld * ncol) return;
+  const int64_t r = idx % ld;
+  const bool ok = r < n_real;
+  const double v = ok ? x[idx] : 0.0;
+  if (e) e[idx] = ok ? (float)exp(scale * v) : 0.0f;
+  if (l) l[idx] = (float)v;
+}
+
+// A32[i,m] = U[i,m] * d[m] * (rs ? rs[i] : 1);  rows >= n_real are zero
+__global__ void stage_factor_kernel(int64_t n_real, int64_t ld, int M, const double* __restrict__ U,
+                                    const double* __restrict__ d, const float* __restrict__ rs,
+                                    float* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ld * M) return;
+  const int64_t r = idx % ld;
+  const int m = (int)(idx / ld);
+  double v = 0.0;
+  if (r < n_real) v = U[idx] * (d ? d[m] : 1.0) * (rs ? (double)rs[r] : 1.0);
+  out[idx] = (float)v;
+}
+
+// Z = (Y - W0)/sqrt(W0) with W0 = a_i b_j:  z = y * s_i t_j - 1/(s_i t_j)    (R/fit.R:111-114)
+template <typename YT>
+__global__ void init_z_kernel(int64_t I, int64_t ldI, int64_t J, const YT* __restrict__ Y,
+                              const float* __restrict__ s_row /* ldI x nbatch */, const float* __restrict__ t_col,
+                              const int32_t* __restrict__ batch, float* __restrict__ Z) {
+  const int64_t j = blockIdx.y;
+  const int kb = batch ? batch[j] : 0;
+  const float tj = t_col[j];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ldI; i += (int64_t)gridDim.x * blockDim.x) {
+    float z = 0.0f;
+    if (i < I) {
+      const float st = s_row[(int64_t)kb * ldI + i] * tj;
+      z = (float)Y[j * ldI + i] * st - 1.0f / st;
+    }
+    Z[j * ldI + i] = z;
+  }
+}
+
+// W[i, j] = exp(alpha_i,b(j) + beta_j + X_ij) in fp64 (R/fit.R:189-191), column chunk
+__global__ void write_w_kernel(int64_t I, int64_t ldI, int64_t j0, int64_t jc, int64_t ldJ, int M, int kind,
+                               const double* __restrict__ U, const double* __restrict__ d,
+                               const double* __restrict__ V, const double* __restrict__ alpha,
+                               const double* __restrict__ beta, const int32_t* __restrict__ batch,
+                               const double* __restrict__ alpha0, const double* __restrict__ beta0,
+                               double* __restrict__ W) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= I * jc) return;
+  const int64_t i = idx % I, jl = idx / I, j = j0 + jl;
+  const int kb = batch ? batch[j] : 0;
+  double x = 0.0;
+  if (kind != XK_ZERO) {
+    for (int m = 0; m < M; ++m) x += U[(int64_t)m * ldI + i] * d[m] * V[(int64_t)m * ldJ + j];
+    if (kind == XK_X0) {
+      x *= exp(-0.5 * (alpha0[(int64_t)kb * ldI + i] + beta0[j]));
+      x = x > 8.0 ? 8.0 : x;
+      x = x < -8.0 ? -8.0 : x;
+    }
+  }
+  W[jl * I + i] = exp(alpha[(int64_t)kb * ldI + i] + x) * exp(beta[j]);
+}
+
+__global__ void f32_to_f64_kernel(int64_t n, const float* __restrict__ a, double* __restrict__ b) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) b[i] = (double)a[i];
+}
+
+__global__ void colsum_batch_total_kernel(int64_t I, int64_t ldI, int nbatch, const double* __restrict__ rowsum,
+                                          double* __restrict__ logtot) {
+  // logtot[k] = log(sum_i rowsum[i,k])  == log(sum(exp(betas[batch==k])))  (R/fit.R:107)
+  __shared__ double red[1024];
+  for (int k = 0; k < nbatch; ++k) {
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < I; i += 1024) s += rowsum[k * ldI + i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int st = 512; st > 0; st >>= 1) {
+      if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) logtot[k] = log(red[0]);
+    __syncthreads();
+  }
+}
+
+__global__ void min_kernel(int64_t n, const double* __restrict__ x, int64_t n_real, int64_t ld, double* __restrict__ out) {
+  // out[0] = min over real entries (single CTA)
+  __shared__ double red[1024];
+  double m = 1e300;
+  for (int64_t idx = threadIdx.x; idx < n; idx += 1024) {
+    if (idx % ld < n_real) m = fmin(m, x[idx]);
+  }
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int st = 512; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] = fmin(red[threadIdx.x], red[threadIdx.x + st]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0];
+}
+
+#define GRID1(n) (unsigned)ceil_div((n), 256), 256, 0, ctx.stream
+
+// ---------------------------------------------------------------------------------
+struct FitState {
+  Ctx& ctx;
+  const scgbm_fit_args& a;
+  Counts Y;
+  int64_t I, J, ldI, ldJ, J_total;
+  int nbatch, M;
+  DevBuf<float> R;
+  DevBuf<double> alpha, beta, alpha0, beta0, logrs, logcs, S, Ccol, logtot, shift, scal;
+  DevBuf<float> f_row, la_row, g_col, lb_col, s_row, t_col;
+  Factor slot[3];
+  EtaWs eta;
+  TsvdWs svd;
+  double maxY = 0;
+  PassGeom geom;
+
+  FitState(Ctx& c, const scgbm_fit_args& args) : ctx(c), a(args) {}
+
+  XDesc desc(const Factor& f) const {
+    XDesc x;
+    if (f.kind == XK_ZERO) { x.M = 0; return x; }
+    x.A = f.A32.get(); x.B = f.B32.get(); x.M = f.M;
+    if (f.kind == XK_X0) {
+      x.clamp = 1;
+      x.rowscale = nbatch > 1 ? s_row.get() : nullptr;
+    }
+    return x;
+  }
+
+  void stage_cols() {   // g_col = exp(beta), lb_col = beta
+    ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
+    exp_stage_kernel<<<GRID1(ldJ)>>>(J, ldJ, 1, beta.get(), 1.0, g_col.get(), lb_col.get());
+    SCGBM_LAUNCH_CHECK();
+  }
+  void stage_rows() {   // f_row = exp(alpha), la_row = alpha
+    ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
+    exp_stage_kernel<<<GRID1(ldI * nbatch)>>>(I, ldI, nbatch, alpha.get(), 1.0, f_row.get(), la_row.get());
+    SCGBM_LAUNCH_CHECK();
+  }
+  void stage_factor(Factor& f) {
+    ProfScope ps(ctx.prof, SCGBM_K_MISC, 2);
+    const float* rs = (f.kind == XK_X0 && nbatch == 1) ? s_row.get() : nullptr;
+    const float* cs = (f.kind == XK_X0) ? t_col.get() : nullptr;
+    stage_factor_kernel<<<GRID1(ldI * f.M)>>>(I, ldI, f.M, f.U.get(), f.d.get(), rs, f.A32.get());
+    stage_factor_kernel<<<GRID1(ldJ * f.M)>>>(J, ldJ, f.M, f.V.get(), nullptr, cs, f.B32.get());
+    SCGBM_LAUNCH_CHECK();
+  }
+
+  void setup() {
+    I = a.I; J = a.J; M = a.M; nbatch = a.batch ? std::max(1, a.nbatch) : 1;
+    load_counts(ctx, a.Y, a.y_dtype, a.y_on_device, I, J, a.ldY, a.batch, nbatch, a.y_storage, Y);
+    ldI = Y.ld; ldJ = round_up(J, kRowPad);
+    geom = PassGeom{I, J, ldI, ldJ, nbatch, Y.batch.get()};
+    // global stats
+    scal.alloc(8);
+    double h[2] = {(double)J, Y.maxY};
+    if (ctx.nranks > 1) {
+      SCGBM_CUDA(cudaMemcpyAsync(scal.get(), h, sizeof(h), cudaMemcpyHostToDevice, ctx.stream));
+      ctx.allreduce_sum(scal.get(), 1);
+      ctx.allreduce_max(scal.get() + 1, 1);
+      ctx.allreduce_sum(Y.rowsum.get(), ldI * nbatch);
+      SCGBM_CUDA(cudaMemcpyAsync(h, scal.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
+      ctx.sync();
+    }
+    J_total = (int64_t)llround(h[0]);
+    maxY = h[1];
+    SCGBM_REQUIRE(M >= 1, "M must be >= 1");
+    SCGBM_REQUIRE(M <= std::min(I, J_total), "M must not exceed min(nrow(Y), ncol(Y))");
+    SCGBM_REQUIRE(maxY > 0.0, "Count matrix Y is all zero");
+
+    R.alloc(ldI * J);
+    alpha.alloc(ldI * nbatch); alpha0.alloc(ldI * nbatch); logrs.alloc(ldI * nbatch); S.alloc(ldI * nbatch);
+    beta.alloc(ldJ); beta0.alloc(ldJ); logcs.alloc(ldJ); Ccol.alloc(ldJ);
+    logtot.alloc(nbatch); shift.alloc(1);
+    f_row.alloc(ldI * nbatch); la_row.alloc(ldI * nbatch); s_row.alloc(ldI * nbatch);
+    g_col.alloc(ldJ); lb_col.alloc(ldJ); t_col.alloc(ldJ);
+    alpha.zero(ctx.stream); beta.zero(ctx.stream); logcs.zero(ctx.stream);
+    for (auto& f : slot) f.alloc(ldI, ldJ, M);
+
+    // Q11 precondition: every gene (per batch) and every cell must have a count
+    {
+      DevBuf<double> mn(2);
+      min_kernel<<<1, 1024, 0, ctx.stream>>>(ldI * nbatch, Y.rowsum.get(), I, ldI, mn.get());
+      min_kernel<<<1, 1024, 0, ctx.stream>>>(J, Y.colsum.get(), J, J, mn.get() + 1);
+      SCGBM_LAUNCH_CHECK();
+      double hm[2];
+      SCGBM_CUDA(cudaMemcpyAsync(hm, mn.get(), sizeof(hm), cudaMemcpyDeviceToHost, ctx.stream));
+      ctx.sync();
+      double bad = (!(hm[0] > 0.0) || !(hm[1] > 0.0)) ? 1.0 : 0.0;
+      if (ctx.nranks > 1) {   // every rank must take the same branch
+        SCGBM_CUDA(cudaMemcpyAsync(mn.get(), &bad, sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+        ctx.allreduce_max(mn.get(), 1);
+        SCGBM_CUDA(cudaMemcpyAsync(&bad, mn.get(), sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+        ctx.sync();
+      }
+      if (bad != 0.0)
+        throw Error(SCGBM_ERR_INVALID,
+                    "every gene (within each batch) and every cell needs at least one count: the reference "
+                    "takes log(rowSums)/log(colSums) (R/fit.R:96,104) and turns NaN otherwise");
+    }
+    ProfScope ps(ctx.prof, SCGBM_K_MISC, 6);
+    // betas = log(colSums(Y))  (R/fit.R:96,99); log.rsy (R/fit.R:102-105)
+    log_kernel<<<GRID1(J)>>>(J, Y.colsum.get(), logcs.get());
+    SCGBM_CUDA(cudaMemcpyAsync(beta.get(), logcs.get(), J * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+    log_kernel<<<GRID1(ldI * nbatch)>>>(ldI * nbatch, Y.rowsum.get(), logrs.get());
+    // alphas = log.rsy - log(sum(exp(betas[batch==k])))  (R/fit.R:106-108); recentre (:109-110)
+    colsum_batch_total_kernel<<<1, 1024, 0, ctx.stream>>>(I, ldI, nbatch, Y.rowsum.get(), logtot.get());
+    alpha_update_kernel<<<1, 1024, 0, ctx.stream>>>(I, ldI, nbatch, logrs.get(), nullptr, logtot.get(), alpha.get(), shift.get());
+    beta_shift_kernel<<<GRID1(J)>>>(J, beta.get(), shift.get());
+    SCGBM_LAUNCH_CHECK();
+    SCGBM_CUDA(cudaMemcpyAsync(alpha0.get(), alpha.get(), ldI * nbatch * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+    SCGBM_CUDA(cudaMemcpyAsync(beta0.get(), beta.get(), ldJ * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+    // s = exp(-alpha0/2), t = exp(-beta0/2): W0^(-1/2) = s_i t_j   (R/fit.R:111,114,117)
+    exp_stage_kernel<<<GRID1(ldI * nbatch)>>>(I, ldI, nbatch, alpha.get(), -0.5, s_row.get(), nullptr);
+    exp_stage_kernel<<<GRID1(ldJ)>>>(J, ldJ, 1, beta.get(), -0.5, t_col.get(), nullptr);
+    SCGBM_LAUNCH_CHECK();
+  }
+
+  void init_svd() {
+    {
+      ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
+      dim3 grid((unsigned)std::min<int64_t>(ceil_div(ldI, 256), 64), 1);
+      const int64_t slab = 65535;
+      for (int64_t j0 = 0; j0 < J; j0 += slab) {
+        grid.y = (unsigned)std::min(slab, J - j0);
+        const int32_t* bt = Y.batch.get() ? Y.batch.get() + j0 : nullptr;
+        float* z = R.get() + j0 * ldI;
+        switch (Y.storage) {
+          case SCGBM_STORE_U8: init_z_kernel<uint8_t><<<grid, 256, 0, ctx.stream>>>(I, ldI, J - j0, (const uint8_t*)Y.data + j0 * ldI, s_row.get(), t_col.get() + j0, bt, z); break;
+          case SCGBM_STORE_U16: init_z_kernel<uint16_t><<<grid, 256, 0, ctx.stream>>>(I, ldI, J - j0, (const uint16_t*)Y.data + j0 * ldI, s_row.get(), t_col.get() + j0, bt, z); break;
+          default: init_z_kernel<float><<<grid, 256, 0, ctx.stream>>>(I, ldI, J - j0, (const float*)Y.data + j0 * ldI, s_row.get(), t_col.get() + j0, bt, z); break;
+        }
+        SCGBM_LAUNCH_CHECK();
+      }
+    }
+    GOperator op;
+    op.I = I; op.ldI = ldI; op.J = J; op.ldJ = ldJ; op.J_total = J_total;
+    op.R = R.get(); op.c = 1.0; op.nterms = 0;
+    TsvdOpts o = opts();
+    Factor& f = slot[0];
+    tsvd(ctx, svd, op, o, f.U.get(), f.d.get(), f.V.get(), nullptr, nullptr);     // R/fit.R:115
+    f.kind = XK_X0;
+    stage_factor(f);                                                                // R/fit.R:116-120
+    // the Pearson-residual right basis stays as the warm start of the first PGD projection
+  }
+
+  TsvdOpts opts() const {
+    TsvdOpts o;
+    o.M = M;
+    o.extra = a.svd_extra > 0 ? a.svd_extra : 12;
+    o.depth = a.svd_depth > 0 ? a.svd_depth : 3;
+    o.tol = a.svd_tol > 0 ? a.svd_tol : 1e-4;
+    o.seed = a.seed;
+    return o;
+  }
+};
+
+static double now_sec() {
+  using namespace std::chrono;
+  return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
+void fit_impl(const scgbm_fit_args* a, scgbm_fit_out* out) {
+  SCGBM_REQUIRE(a && out, "NULL args");
+  SCGBM_REQUIRE(a->I >= 1 && a->J >= 1, "Y must be a non-empty matrix");
+  SCGBM_REQUIRE(a->M >= 1, "M must be >= 1");
+  SCGBM_REQUIRE(a->max_iter >= 1, "max.iter must be >= 1");
+  SCGBM_REQUIRE(out->U && out->D && out->V && out->alpha && out->beta && out->obj, "output buffers missing");
+  Ctx ctx(a->device, reinterpret_cast<Comm*>(a->comm));
+  ctx.prof.timing = a->profile != 0;
+  cudaEvent_t ev0, ev1;
+  SCGBM_CUDA(cudaEventCreate(&ev0));
+  SCGBM_CUDA(cudaEventCreate(&ev1));
+  SCGBM_CUDA(cudaEventRecord(ev0, ctx.stream));
+
+  FitState st(ctx, *a);
+  st.setup();
+  st.init_svd();
+  const int64_t I = st.I, J = st.J, ldI = st.ldI, ldJ = st.ldJ;
+  const int M = st.M, nbatch = st.nbatch;
+  const int max_iter = a->max_iter;
+
+  std::vector<double> LL(max_iter, 0.0);
+  double lr = 1.0;                                       // R/fit.R:84
+  int cur = 0, prev = -1, last = -1;                     // factor slots; prev == -1: Xt = 0 (R/fit.R:123)
+  int n_obj = 0, n_iter = 0, hit_max = 0;
+  double t_prev = now_sec(), t_cum = 0.0;
+  Factor zero_factor;
+  double fused_bytes = 0.0;
+
+  for (int i = 1; i <= max_iter; ++i) {                  // R/fit.R:125
+    n_iter = i;
+    const Factor& fc = st.slot[cur];
+    const XDesc xc = st.desc(fc);
+    // (a) alphas <- log.rsy - log(rowSums(exp(X + betas)))      R/fit.R:127-130
+    st.stage_cols();
+    pass_rowsum(ctx, st.eta, st.geom, xc, st.g_col.get(), st.S.get());
+    ctx.allreduce_sum(st.S.get(), ldI * nbatch);
+    {
+      ProfScope ps(ctx.prof, SCGBM_K_MISC, 2);
+      alpha_update_kernel<<<1, 1024, 0, ctx.stream>>>(I, ldI, nbatch, st.logrs.get(), st.S.get(), nullptr,
+                                                      st.alpha.get(), st.shift.get());
+      beta_shift_kernel<<<GRID1(J)>>>(J, st.beta.get(), st.shift.get());          // R/fit.R:131-132
+      SCGBM_LAUNCH_CHECK();
+    }
+    st.stage_rows();
+    if (a->infer_beta) {                                 // R/fit.R:133-135
+      pass_colsum(ctx, st.eta, st.geom, xc, st.f_row.get(), st.Ccol.get());
+      ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
+      beta_infer_kernel<<<GRID1(J)>>>(J, st.logcs.get(), st.Ccol.get(), st.beta.get());
+      SCGBM_LAUNCH_CHECK();
+    }
+    st.stage_cols();
+    // (d)-(g) W, clip, objective, max W; residual Y - W           R/fit.R:136-151,321
+    pass_fused(ctx, st.eta, st.geom, xc, st.Y, st.f_row.get(), st.g_col.get(), st.la_row.get(), st.lb_col.get(),
+               (float)st.maxY, st.R.get(), st.scal.get());
+    if (fused_bytes == 0.0) {
+      XDesc xm = xc; xm.M = M;
+      fused_bytes = fused_pass_bytes(st.geom, xm, st.Y.elem_bytes());
+    }
+    ctx.allreduce_sum(st.scal.get(), 2);
+    ctx.allreduce_max(st.scal.get() + 2, 1);
+    double h[3];
+    SCGBM_CUDA(cudaMemcpyAsync(h, st.scal.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+    if (a->time_by_iter && out->time) {                  // R/fit.R:139-142
+      const double t = now_sec();
+      t_cum += t - t_prev; t_prev = t;
+      out->time[i - 1] = t_cum;
+    }
+    const double ll = h[1] - h[0];                       // R/fit.R:151
+    const double w_max = h[2];
+    LL[i - 1] = ll;
+    if (out->LL) out->LL[i - 1] = ll;
+    if (out->accepted) out->accepted[i - 1] = 0;
+    if (a->verbose) fprintf(stderr, "[scgbm] iter %d LL=%.10g lr=%.4g wmax=%.6g\n", i, ll, lr, w_max);
+
+    if (std::isnan(ll) || std::isinf(ll)) {              // R/fit.R:152-157
+      if (prev >= 0) cur = prev; else { cur = -2; }      // X <- Xt
+      lr = lr / 2;
+      if (cur == -2) {                                   // Xt is the zero matrix (only before the first accept)
+        st.slot[2].kind = XK_ZERO; st.slot[2].M = M; cur = 2;
+      }
+      continue;
+    }
+    if (i >= 3) {                                        // R/fit.R:158
+      const double tau = std::fabs((ll - LL[i - 3]) / ll);
+      if (tau < a->tol && lr <= 1.06 && i >= a->min_iter) break;        // R/fit.R:160-162
+      const double llp = LL[i - 2];
+      if (std::isnan(llp))                               // quirk Q1: if (NA) errors in R
+        throw Error(SCGBM_ERR_NUMERIC, "missing value where TRUE/FALSE needed (objective was NaN at the previous iteration)");
+      if (ll < llp) {                                    // R/fit.R:164-167
+        lr = std::max(lr / 2, 1.0);
+        if (prev >= 0) cur = prev;
+        else { st.slot[2].kind = XK_ZERO; st.slot[2].M = M; cur = 2; }
+        continue;
+      } else {
+        lr = lr * 1.05;                                  // R/fit.R:169
+      }
+    }
+    out->obj[n_obj++] = ll;                              // R/fit.R:174
+    if (out->accepted) out->accepted[i - 1] = 1;
+    if (a->progress) a->progress(i, ll, a->progress_user);   // R/fit.R:175
+
+    // (k) pgd_irlba                                               R/fit.R:315-328
+    const double m = (double)(i - 1) / (double)(i + 2);  // R/fit.R:319
+    const double c = lr / w_max;                         // R/fit.R:321,323
+    GOperator op;
+    op.I = I; op.ldI = ldI; op.J = J; op.ldJ = ldJ; op.J_total = st.J_total;
+    op.R = st.R.get(); op.c = c; op.nterms = 0;
+    auto add_term = [&](int s, double coef) {
+      if (s < 0 || coef == 0.0) return;
+      Factor& f = st.slot[s];
+      if (f.kind == XK_ZERO) return;
+      if (f.kind == XK_X0) {                             // clamped X0 is not low-rank: fold it into R
+        pass_addx(ctx, st.geom, st.desc(f), (float)(coef / c), st.R.get());
+        return;
+      }
+      LowRankTerm& t = op.t[op.nterms++];
+      t.A = f.U.get(); t.lda = ldI; t.d = f.d.get(); t.B = f.V.get(); t.ldb = ldJ; t.M = f.M; t.coef = coef;
+    };
+    if (prev == cur || m == 0.0) add_term(cur, 1.0);     // X == Xt right after a revert (Q4)
+    else { add_term(cur, 1.0 + m); add_term(prev, -m); }
+    int next = 0;
+    while (next == cur || next == prev) ++next;
+    Factor& fn = st.slot[next];
+    fn.kind = XK_LOWRANK; fn.M = M;
+    TsvdOpts o = st.opts();
+    tsvd(ctx, st.svd, op, o, fn.U.get(), fn.d.get(), fn.V.get(), nullptr, nullptr);   // R/fit.R:323
+    st.stage_factor(fn);                                 // X <- u d v^T (never materialised; R/fit.R:324)
+    prev = cur; cur = next; last = next;                 // R/fit.R:179-180,320
+    if (i == max_iter) hit_max = 1;                      // R/fit.R:182-185
+  }
+  if (last < 0)
+    throw Error(SCGBM_ERR_NUMERIC, "no projected-gradient step was taken (object 'pgd' not found in the reference)");
+
+  // ---- assemble (R/fit.R:188-204, 301-313) -------------------------------------
+  out->n_obj = n_obj; out->n_iter = n_iter; out->hit_max_iter = hit_max;
+  out->y_storage = st.Y.storage; out->max_Y = st.maxY;
+  const Factor& fl = st.slot[last];
+  std::vector<double> hU((size_t)ldI * M), hV((size_t)ldJ * M), hD(M), hA((size_t)ldI * nbatch), hB(ldJ);
+  SCGBM_CUDA(cudaMemcpyAsync(hU.data(), fl.U.get(), hU.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  SCGBM_CUDA(cudaMemcpyAsync(hV.data(), fl.V.get(), hV.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  SCGBM_CUDA(cudaMemcpyAsync(hD.data(), fl.d.get(), M * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  SCGBM_CUDA(cudaMemcpyAsync(hA.data(), st.alpha.get(), hA.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  SCGBM_CUDA(cudaMemcpyAsync(hB.data(), st.beta.get(), hB.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  ctx.prof.d2h_bytes += (double)(hU.size() + hV.size() + hA.size() + hB.size()) * sizeof(double);
+  // sign convention: the FIRST gene of the GLOBAL matrix decides; U is replicated so every rank agrees
+  for (int m2 = 0; m2 < M; ++m2) {
+    const bool flip = hU[(size_t)m2 * ldI + 0] < 0;                       // R/fit.R:305
+    for (int64_t i2 = 0; i2 < I; ++i2) {
+      const double u = hU[(size_t)m2 * ldI + i2];
+      if (out->loadings) out->loadings[(size_t)m2 * I + i2] = u;          // pre-flip (Q7, R/fit.R:196)
+      out->U[(size_t)m2 * I + i2] = flip ? -u : u;
+    }
+    for (int64_t j2 = 0; j2 < J; ++j2) {
+      const double v = hV[(size_t)m2 * ldJ + j2];
+      const double vf = flip ? -v : v;
+      out->V[(size_t)m2 * J + j2] = vf;
+      if (out->scores) out->scores[(size_t)m2 * J + j2] = vf * hD[m2];    // R/fit.R:310
+    }
+    out->D[m2] = hD[m2];
+  }
+  for (int k = 0; k < nbatch; ++k)
+    for (int64_t i2 = 0; i2 < I; ++i2) out->alpha[(size_t)k * I + i2] = hA[(size_t)k * ldI + i2];
+  for (int64_t j2 = 0; j2 < J; ++j2) out->beta[j2] = hB[j2];
+
+  if (a->return_W && out->W) {                           // R/fit.R:189-191 (unclipped, current X)
+    const Factor& fc = st.slot[cur];
+    int64_t jc_max = std::max<int64_t>(1, (int64_t)(64ll << 20) / I);
+    jc_max = std::min(jc_max, J);
+    DevBuf<double> Wd(I * jc_max);
+    for (int64_t j0 = 0; j0 < J; j0 += jc_max) {
+      const int64_t jc = std::min(jc_max, J - j0);
+      {
+        ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
+        write_w_kernel<<<GRID1(I * jc)>>>(I, ldI, j0, jc, ldJ, fc.M, fc.kind, fc.U.get(), fc.d.get(), fc.V.get(),
+                                          st.alpha.get(), st.beta.get(), st.Y.batch.get(), st.alpha0.get(),
+                                          st.beta0.get(), Wd.get());
+        SCGBM_LAUNCH_CHECK();
+      }
+      SCGBM_CUDA(cudaMemcpyAsync(out->W + j0 * I, Wd.get(), I * jc * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+      ctx.sync();
+      ctx.prof.d2h_bytes += (double)I * jc * sizeof(double);
+    }
+  }
+  SCGBM_CUDA(cudaEventRecord(ev1, ctx.stream));
+  ctx.sync();
+  float tot = 0;
+  cudaEventElapsedTime(&tot, ev0, ev1);
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+  memset(&out->prof, 0, sizeof(out->prof));
+  ctx.prof.fill(&out->prof);
+  out->prof.total_ms = tot;
+  out->prof.fused_bytes = fused_bytes;
+  out->prof.svd_passes = st.svd.passes_total;
+  out->prof.svd_calls = st.svd.calls;
+}
+
+}  // namespace scgbm
+
+// ---------------------------------------------------------------------------------
+// diagnostic entry points (kernel-level parity tests)
+// ---------------------------------------------------------------------------------
+namespace scgbm {
+
+static void upload_padded(Ctx& ctx, const double* host, int64_t rows, int cols, int64_t ld, double* dev) {
+  SCGBM_CUDA(cudaMemsetAsync(dev, 0, (size_t)ld * cols * sizeof(double), ctx.stream));
+  SCGBM_CUDA(cudaMemcpy2DAsync(dev, ld * sizeof(double), host, rows * sizeof(double), rows * sizeof(double), cols,
+                               cudaMemcpyHostToDevice, ctx.stream));
+}
+
+void dbg_eval_impl(const scgbm_eval_args* a, scgbm_eval_out* out) {
+  SCGBM_REQUIRE(a && out && a->Y && a->beta_in && out->alpha && out->beta, "NULL args");
+  Ctx ctx(a->device, nullptr);
+  Counts Y;
+  load_counts(ctx, a->Y, a->y_dtype, 0, a->I, a->J, a->ldY, nullptr, 1, a->y_storage, Y);
+  const int64_t I = a->I, J = a->J, ldI = Y.ld, ldJ = round_up(J, kRowPad);
+  const int Mx = a->Mx;
+  PassGeom geom{I, J, ldI, ldJ, 1, nullptr};
+  DevBuf<double> Xu(std::max<int64_t>(ldI * Mx, 1)), Xv(std::max<int64_t>(ldJ * Mx, 1)), alpha(ldI), beta(ldJ),
+      logrs(ldI), logcs(ldJ), S(ldI), Cc(ldJ), shift(1), scal(4), tmp(std::max(ldI, ldJ));
+  DevBuf<float> A32(std::max<int64_t>(ldI * Mx, 1)), B32(std::max<int64_t>(ldJ * Mx, 1)), f_row(ldI), la_row(ldI),
+      g_col(ldJ), lb_col(ldJ), rs32(ldI), cs32(ldJ), R(ldI * J);
+  alpha.zero(ctx.stream); beta.zero(ctx.stream);
+  SCGBM_CUDA(cudaMemcpyAsync(beta.get(), a->beta_in, J * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  XDesc x;
+  if (Mx > 0) {
+    upload_padded(ctx, a->Xu, I, Mx, ldI, Xu.get());
+    upload_padded(ctx, a->Xv, J, Mx, ldJ, Xv.get());
+    const float* rs = nullptr; const float* cs = nullptr;
+    if (a->rowscale) {
+      upload_padded(ctx, a->rowscale, I, 1, ldI, tmp.get());
+      exp_stage_kernel<<<GRID1(ldI)>>>(I, ldI, 1, tmp.get(), 1.0, nullptr, rs32.get());
+      rs = rs32.get();
+    }
+    stage_factor_kernel<<<GRID1(ldI * Mx)>>>(I, ldI, Mx, Xu.get(), nullptr, rs, A32.get());
+    if (a->colscale) {
+      upload_padded(ctx, a->colscale, J, 1, ldJ, tmp.get());
+      exp_stage_kernel<<<GRID1(ldJ)>>>(J, ldJ, 1, tmp.get(), 1.0, nullptr, cs32.get());
+      cs = cs32.get();
+    }
+    stage_factor_kernel<<<GRID1(ldJ * Mx)>>>(J, ldJ, Mx, Xv.get(), nullptr, cs, B32.get());
+    SCGBM_LAUNCH_CHECK();
+    x.A = A32.get(); x.B = B32.get(); x.M = Mx; x.clamp = a->clamp8;
+  }
+  EtaWs eta;
+  log_kernel<<<GRID1(J)>>>(J, Y.colsum.get(), logcs.get());
+  log_kernel<<<GRID1(ldI)>>>(ldI, Y.rowsum.get(), logrs.get());
+  exp_stage_kernel<<<GRID1(ldJ)>>>(J, ldJ, 1, beta.get(), 1.0, g_col.get(), lb_col.get());
+  pass_rowsum(ctx, eta, geom, x, g_col.get(), S.get());
+  alpha_update_kernel<<<1, 1024, 0, ctx.stream>>>(I, ldI, 1, logrs.get(), S.get(), nullptr, alpha.get(), shift.get());
+  beta_shift_kernel<<<GRID1(J)>>>(J, beta.get(), shift.get());
+  exp_stage_kernel<<<GRID1(ldI)>>>(I, ldI, 1, alpha.get(), 1.0, f_row.get(), la_row.get());
+  if (a->infer_beta) {
+    pass_colsum(ctx, eta, geom, x, f_row.get(), Cc.get());
+    beta_infer_kernel<<<GRID1(J)>>>(J, logcs.get(), Cc.get(), beta.get());
+  }
+  exp_stage_kernel<<<GRID1(ldJ)>>>(J, ldJ, 1, beta.get(), 1.0, g_col.get(), lb_col.get());
+  pass_fused(ctx, eta, geom, x, Y, f_row.get(), g_col.get(), la_row.get(), lb_col.get(), (float)Y.maxY, R.get(), scal.get());
+  double h[3];
+  SCGBM_CUDA(cudaMemcpyAsync(h, scal.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
+  SCGBM_CUDA(cudaMemcpyAsync(out->alpha, alpha.get(), I * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  SCGBM_CUDA(cudaMemcpyAsync(out->beta, beta.get(), J * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  out->sum_w = h[0]; out->sum_ylogw = h[1]; out->max_w = h[2]; out->max_Y = Y.maxY; out->LL = h[1] - h[0];
+  if (out->resid) {
+    DevBuf<double> Rd(ldI * J);
+    f32_to_f64_kernel<<<GRID1(ldI * J)>>>(ldI * J, R.get(), Rd.get());
+    SCGBM_LAUNCH_CHECK();
+    SCGBM_CUDA(cudaMemcpy2DAsync(out->resid, I * sizeof(double), Rd.get(), ldI * sizeof(double), I * sizeof(double), J,
+                                 cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+  }
+}
+
+void dbg_tsvd_impl(const scgbm_tsvd_args* a, scgbm_tsvd_out* out) {
+  SCGBM_REQUIRE(a && out && out->U && out->D && out->V, "NULL args");
+  SCGBM_REQUIRE(a->nterms >= 0 && a->nterms <= 2, "nterms must be 0..2");
+  Ctx ctx(a->device, nullptr);
+  const int64_t I = a->I, J = a->J, ldI = round_up(I, kRowPad), ldJ = round_up(J, kRowPad);
+  const int M = a->M;
+  GOperator op;
+  op.I = I; op.ldI = ldI; op.J = J; op.ldJ = ldJ; op.J_total = J;
+  DevBuf<float> R;
+  if (a->R) {
+    R.alloc(ldI * J);
+    R.zero(ctx.stream);
+    SCGBM_CUDA(cudaMemcpy2DAsync(R.get(), ldI * sizeof(float), a->R, I * sizeof(float), I * sizeof(float), J,
+                                 cudaMemcpyHostToDevice, ctx.stream));
+    op.R = R.get(); op.c = a->c;
+  }
+  DevBuf<double> tA[2], td[2], tB[2];
+  for (int t = 0; t < a->nterms; ++t) {
+    const int Mt = a->Mt[t];
+    tA[t].alloc(ldI * Mt); td[t].alloc(Mt); tB[t].alloc(ldJ * Mt);
+    upload_padded(ctx, a->A[t], I, Mt, ldI, tA[t].get());
+    upload_padded(ctx, a->B[t], J, Mt, ldJ, tB[t].get());
+    SCGBM_CUDA(cudaMemcpyAsync(td[t].get(), a->d[t], Mt * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+    LowRankTerm& lt = op.t[op.nterms++];
+    lt.A = tA[t].get(); lt.lda = ldI; lt.d = td[t].get(); lt.B = tB[t].get(); lt.ldb = ldJ; lt.M = Mt; lt.coef = a->coef[t];
+  }
+  TsvdOpts o;
+  o.M = M;
+  o.extra = a->svd_extra > 0 ? a->svd_extra : 12;
+  o.depth = a->svd_depth > 0 ? a->svd_depth : 3;
+  o.tol = a->svd_tol > 0 ? a->svd_tol : 1e-4;
+  o.seed = a->seed;
+  o.variant = a->kernel_variant;
+  TsvdWs ws;
+  if (a->V0) {
+    const int b = (int)std::min<int64_t>(M + o.extra, std::min(I, J));
+    ws.b = b;
+    int depth = (int)std::min<int64_t>(o.depth, std::max<int64_t>(0, std::min(I, J) / b - 1));
+    const int pmax = b * (depth + 1);
+    ws.Qb.alloc(ldI * pmax); ws.Zb.alloc(ldJ * pmax); ws.Kb.alloc(ldI * b);
+    ws.tmpI.alloc(ldI * b); ws.tmpJ.alloc(ldJ * b);
+    ws.T.alloc((int64_t)pmax * pmax); ws.Tw.alloc((int64_t)pmax * pmax); ws.S.alloc((int64_t)pmax * pmax);
+    ws.theta.alloc(pmax); ws.est.alloc(2);
+    ws.Ub.alloc(ldI * b); ws.Vb.alloc(ldJ * b); ws.Vwarm.alloc(ldJ * b);
+    upload_padded(ctx, a->V0, J, b, ldJ, ws.Vwarm.get());
+    ws.warm = true;
+  }
+  DevBuf<double> U(ldI * M), D(M), V(ldJ * M);
+  int passes = 0;
+  double est = 0;
+  tsvd(ctx, ws, op, o, U.get(), D.get(), V.get(), &passes, &est);
+  SCGBM_CUDA(cudaMemcpy2DAsync(out->U, I * sizeof(double), U.get(), ldI * sizeof(double), I * sizeof(double), M,
+                               cudaMemcpyDeviceToHost, ctx.stream));
+  SCGBM_CUDA(cudaMemcpy2DAsync(out->V, J * sizeof(double), V.get(), ldJ * sizeof(double), J * sizeof(double), M,
+                               cudaMemcpyDeviceToHost, ctx.stream));
+  SCGBM_CUDA(cudaMemcpyAsync(out->D, D.get(), M * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  out->passes = passes;
+  out->est = est;
+}
+
+}  // namespace scgbm

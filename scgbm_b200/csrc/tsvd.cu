@@ -1,0 +1,242 @@
+// tsvd.cu -- host-sequenced block-Krylov truncated SVD; all arithmetic on device.
+//
+// One cycle, started from a cell-side block V0 (J x b; the previous iteration's right
+// Ritz vectors when warm, Gaussian when cold):
+//     Q_0 = orth(G V0)
+//     for t = 0..depth:   Z_t = G^T Q_t ;  T = [Z_0..Z_t]^T [Z_0..Z_t]  (= Qb^T G G^T Qb)
+//                         eig(T) -> Ritz values theta, vectors S; stop when the
+//                         residual estimate of the top M pairs is below tol
+//                         Q_{t+1} = orth(G Z_t  minus span(Q_0..Q_t))
+//     U = Qb S,  D = sqrt(theta),  V = Zb S theta^{-1/2}
+// G is touched 2 + 2t times; the gene-side basis (I x p) is replicated on every rank,
+// the cell-side blocks (J x p) are sharded, and only I x b partial products and the
+// p x b Gram blocks cross NVLink.  Cold starts restart the cycle from the Ritz block.
+#include "tsvd.cuh"
+
+namespace scgbm {
+
+__global__ void fill_normal_kernel(int64_t n, int q, int64_t ld, uint64_t seed, uint64_t row_offset,
+                                   double* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * q) return;
+  const int64_t r = idx % n;
+  const int c = (int)(idx / n);
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)((row_offset + r) * 1024 + c + 1);
+  auto mix = [](uint64_t x) {
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+  };
+  const uint64_t a = mix(z), b = mix(z + 0x632BE59BD9B4E019ull);
+  const double u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  const double u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  out[(int64_t)c * ld + r] = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+// C[m,k] *= coef * d[m]
+__global__ void scale_rows_kernel(int M, int b, double* __restrict__ C, const double* __restrict__ d, double coef) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * b) return;
+  C[idx] *= coef * d[idx % M];
+}
+
+// scatter the contiguous block column Cblk (p x b) into T (ldT) at columns [tb, tb+b)
+// and mirror it into rows [tb, tb+b)
+__global__ void scatter_T_kernel(int p, int b, int tb, const double* __restrict__ Cblk, double* __restrict__ T, int ldT) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p * b) return;
+  const int r = idx % p, k = idx / p;
+  const double v = Cblk[idx];
+  T[(int64_t)(tb + k) * ldT + r] = v;
+  T[(int64_t)r * ldT + tb + k] = v;
+}
+
+__global__ void copy_lead_kernel(int p, const double* __restrict__ T, int ldT, double* __restrict__ Tw) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p * p) return;
+  const int r = idx % p, c = idx / p;
+  Tw[idx] = T[(int64_t)c * ldT + r];
+}
+
+// est = max_{k<M} sqrt(s_kt^T T_tt s_kt) * sqrt(theta_0) / theta_k
+__global__ void ritz_est_kernel(int p, int b, int tb, int M, const double* __restrict__ S,
+                                const double* __restrict__ theta, const double* __restrict__ T, int ldT,
+                                double* __restrict__ est) {
+  __shared__ double red[64];
+  double e = 0.0;
+  for (int k = threadIdx.x; k < M; k += blockDim.x) {
+    const double* s = S + (int64_t)k * p + tb;
+    double q = 0.0;
+    for (int c = 0; c < b; ++c) {
+      double col = 0.0;
+      for (int r = 0; r < b; ++r) col += s[r] * T[(int64_t)(tb + c) * ldT + tb + r];
+      q += col * s[c];
+    }
+    const double th = theta[k];
+    const double v = (th > 0.0) ? sqrt(fmax(q, 0.0)) * sqrt(fmax(theta[0], 0.0)) / th : 0.0;
+    e = fmax(e, v);
+  }
+  e = warp_max(e);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+    est[0] = m;
+    est[1] = theta[0];
+  }
+}
+
+// Sv[:,k] = S[:,k] / sqrt(theta_k)  (zero when theta_k <= tiny), D[k] = sqrt(theta_k)
+__global__ void ritz_scale_kernel(int p, int b, const double* __restrict__ S, const double* __restrict__ theta,
+                                  double* __restrict__ Sv, double* __restrict__ Dall) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p * b) return;
+  const int k = idx / p;
+  const double th = theta[k];
+  const double ok = th > 1e-300 * fmax(theta[0], 1e-300) && th > 0.0;
+  Sv[idx] = ok ? S[idx] * rsqrt(th) : 0.0;
+  if (idx % p == 0) Dall[k] = th > 0.0 ? sqrt(th) : 0.0;
+}
+
+// ---------------------------------------------------------------------------------
+static void op_mul(Ctx& ctx, TsvdWs& ws, const GOperator& op, const double* P, int64_t ldP, int b, double* out,
+                   int variant) {
+  // out (ldI x b) = G P, summed over ranks
+  SCGBM_CUDA(cudaMemsetAsync(out, 0, (size_t)op.ldI * b * sizeof(double), ctx.stream));
+  for (int t = 0; t < op.nterms; ++t) {
+    const LowRankTerm& lt = op.t[t];
+    if (lt.M == 0 || lt.coef == 0.0) continue;
+    double* C = ws.C.get();
+    ts_gram(ctx, ws.small, op.J, lt.M, b, lt.B, lt.ldb, P, ldP, C, lt.M, 1.0, 0.0);
+    {
+      ProfScope ps(ctx.prof, SCGBM_K_SMALL, 1);
+      scale_rows_kernel<<<(unsigned)ceil_div(lt.M * b, 256), 256, 0, ctx.stream>>>(lt.M, b, C, lt.d, lt.coef);
+      SCGBM_LAUNCH_CHECK();
+    }
+    ts_mul(ctx, op.ldI, lt.M, b, lt.A, lt.lda, C, lt.M, out, op.ldI, 1.0, 1.0);
+  }
+  if (op.R && op.c != 0.0) prod_n(ctx, ws.prod, op.R, op.I, op.ldI, op.J, P, ldP, b, op.c, out, op.ldI, variant);
+  ctx.allreduce_sum(out, op.ldI * b);
+}
+
+static void op_tmul(Ctx& ctx, TsvdWs& ws, const GOperator& op, const double* Q, int64_t ldQ, int b, double* out,
+                    int variant) {
+  // out (ldJ x b) = G^T Q  (local cells)
+  SCGBM_CUDA(cudaMemsetAsync(out, 0, (size_t)op.ldJ * b * sizeof(double), ctx.stream));
+  for (int t = 0; t < op.nterms; ++t) {
+    const LowRankTerm& lt = op.t[t];
+    if (lt.M == 0 || lt.coef == 0.0) continue;
+    double* C = ws.C.get();
+    ts_gram(ctx, ws.small, op.ldI, lt.M, b, lt.A, lt.lda, Q, ldQ, C, lt.M, 1.0, 0.0);
+    {
+      ProfScope ps(ctx.prof, SCGBM_K_SMALL, 1);
+      scale_rows_kernel<<<(unsigned)ceil_div(lt.M * b, 256), 256, 0, ctx.stream>>>(lt.M, b, C, lt.d, lt.coef);
+      SCGBM_LAUNCH_CHECK();
+    }
+    ts_mul(ctx, op.J, lt.M, b, lt.B, lt.ldb, C, lt.M, out, op.ldJ, 1.0, 1.0);
+  }
+  if (op.R && op.c != 0.0) prod_t(ctx, ws.prod, op.R, op.I, op.ldI, op.J, Q, ldQ, b, op.c, out, op.ldJ, variant);
+}
+
+void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* outU, double* outD,
+          double* outV, int* passes_out, double* est_out) {
+  const int M = o.M;
+  const int64_t minIJ = std::min(op.I, op.J_total);
+  SCGBM_REQUIRE(M >= 1 && M <= minIJ, "M must be between 1 and min(I, J)");
+  int b = (int)std::min<int64_t>(M + std::max(o.extra, 0), minIJ);
+  int depth = std::max(0, o.depth);
+  // keep the Krylov basis inside the space: b * (depth + 1) <= min(I, J)
+  depth = (int)std::min<int64_t>(depth, std::max<int64_t>(0, minIJ / b - 1));
+  const int pmax = b * (depth + 1);
+  const int64_t ldI = op.ldI, ldJ = op.ldJ;
+  int maxM = 1;
+  for (int t = 0; t < op.nterms; ++t) maxM = std::max(maxM, op.t[t].M);
+
+  if (ws.b != b || ws.Zb.n < ldJ * pmax || ws.Qb.n < ldI * pmax) {
+    ws.b = b;
+    ws.warm = false;
+    ws.Qb.alloc(ldI * pmax); ws.Zb.alloc(ldJ * pmax); ws.Kb.alloc(ldI * b);
+    ws.tmpI.alloc(ldI * b); ws.tmpJ.alloc(ldJ * b);
+    ws.T.alloc((int64_t)pmax * pmax); ws.Tw.alloc((int64_t)pmax * pmax); ws.S.alloc((int64_t)pmax * pmax);
+    ws.theta.alloc(pmax); ws.est.alloc(2);
+    ws.Ub.alloc(ldI * b); ws.Vb.alloc(ldJ * b); ws.Vwarm.alloc(ldJ * b);
+  }
+  if (ws.C.n < (int64_t)std::max(maxM, pmax) * b) ws.C.alloc((int64_t)std::max(maxM, pmax) * b);
+  // pad rows of the gene-side buffers must be zero for prod_t's operand conversion
+  ws.Qb.zero(ctx.stream); ws.Kb.zero(ctx.stream);
+
+  int passes = 0;
+  double est = 1e300;
+  const double* V0 = nullptr;
+  if (ws.warm) {
+    V0 = ws.Vwarm.get();
+  } else {
+    ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
+    fill_normal_kernel<<<(unsigned)ceil_div(op.J * b, 256), 256, 0, ctx.stream>>>(
+        op.J, b, ldJ, o.seed, (uint64_t)ctx.rank << 40, ws.Vb.get());
+    SCGBM_LAUNCH_CHECK();
+    V0 = ws.Vb.get();
+  }
+  const bool was_warm = ws.warm;
+  int p = b;
+  for (int cycle = 0;; ++cycle) {
+    ws.T.zero(ctx.stream);
+    op_mul(ctx, ws, op, V0, ldJ, b, ws.Qb.get(), o.variant);
+    ++passes;
+    sym_orth(ctx, ws.small, ldI, b, ws.Qb.get(), ldI, nullptr, ldI, 0, ws.tmpI.get());
+    int t = 0;
+    for (;; ++t) {
+      p = b * (t + 1);
+      double* Zt = ws.Zb.get() + (int64_t)t * b * ldJ;
+      op_tmul(ctx, ws, op, ws.Qb.get() + (int64_t)t * b * ldI, ldI, b, Zt, o.variant);
+      ++passes;
+      // Gram block column  Zb[:, :p]^T Z_t  (p x b), all ranks
+      ts_gram(ctx, ws.small, op.J, p, b, ws.Zb.get(), ldJ, Zt, ldJ, ws.C.get(), p, 1.0, 0.0);
+      ctx.allreduce_sum(ws.C.get(), (int64_t)p * b);
+      {
+        ProfScope ps(ctx.prof, SCGBM_K_SMALL, 2);
+        scatter_T_kernel<<<(unsigned)ceil_div(p * b, 256), 256, 0, ctx.stream>>>(p, b, t * b, ws.C.get(), ws.T.get(), pmax);
+        copy_lead_kernel<<<(unsigned)ceil_div(p * p, 256), 256, 0, ctx.stream>>>(p, ws.T.get(), pmax, ws.Tw.get());
+        SCGBM_LAUNCH_CHECK();
+      }
+      eigh_desc(ctx, ws.small, p, ws.Tw.get(), ws.theta.get(), ws.S.get());
+      {
+        ProfScope ps(ctx.prof, SCGBM_K_SMALL, 1);
+        ritz_est_kernel<<<1, 64, 0, ctx.stream>>>(p, b, t * b, M, ws.S.get(), ws.theta.get(), ws.T.get(), pmax, ws.est.get());
+        SCGBM_LAUNCH_CHECK();
+      }
+      double h[2];
+      SCGBM_CUDA(cudaMemcpyAsync(h, ws.est.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
+      ctx.sync();
+      est = h[0];
+      if (!(h[1] == h[1])) throw Error(SCGBM_ERR_NUMERIC, "truncated SVD: non-finite Ritz values");
+      if (t > 0 && est < o.tol) break;
+      if (t >= depth) break;
+      op_mul(ctx, ws, op, Zt, ldJ, b, ws.Qb.get() + (int64_t)(t + 1) * b * ldI, o.variant);
+      ++passes;
+      sym_orth(ctx, ws.small, ldI, b, ws.Qb.get() + (int64_t)(t + 1) * b * ldI, ldI, ws.Qb.get(), ldI, p, ws.tmpI.get());
+    }
+    // Ritz vectors of the leading b pairs
+    {
+      ProfScope ps(ctx.prof, SCGBM_K_SMALL, 1);
+      ritz_scale_kernel<<<(unsigned)ceil_div(p * b, 256), 256, 0, ctx.stream>>>(p, b, ws.S.get(), ws.theta.get(), ws.C.get(), ws.Tw.get());
+      SCGBM_LAUNCH_CHECK();
+    }
+    ts_mul(ctx, ldI, p, b, ws.Qb.get(), ldI, ws.S.get(), p, ws.Ub.get(), ldI, 1.0, 0.0);
+    ts_mul(ctx, op.J, p, b, ws.Zb.get(), ldJ, ws.C.get(), p, ws.Vwarm.get(), ldJ, 1.0, 0.0);
+    const bool converged = est < o.tol || depth == 0;
+    if (converged || cycle + 1 >= o.max_cycles || (was_warm && cycle >= 1)) break;
+    V0 = ws.Vwarm.get();
+  }
+  ws.warm = true;
+  copy_mat(ctx, ldI, M, ws.Ub.get(), ldI, outU, ldI);
+  copy_mat(ctx, op.J, M, ws.Vwarm.get(), ldJ, outV, ldJ);
+  SCGBM_CUDA(cudaMemcpyAsync(outD, ws.Tw.get(), M * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+  ws.passes_total += passes;
+  ws.calls += 1;
+  if (passes_out) *passes_out = passes;
+  if (est_out) *est_out = est;
+}
+
+}  // namespace scgbm

@@ -1,0 +1,54 @@
+// tsvd.cuh -- warm-started, restarted block-Krylov truncated SVD of the operator
+//     G = sum_t coef_t * A_t diag(d_t) B_t^T  +  c * R
+// (low-rank terms exact in fp64 through their factors, R the materialised fp32
+// residual).  Replaces irlba::irlba(V + (lr/w.max)(Y - W), nv = M) at R/fit.R:323 and
+// irlba::irlba(Z, nv = M) at R/fit.R:115.
+#pragma once
+#include "common.cuh"
+#include "dense_small.cuh"
+#include "products.cuh"
+
+namespace scgbm {
+
+struct LowRankTerm {
+  const double* A = nullptr; int64_t lda = 0;   // ldI x M
+  const double* d = nullptr;                    // M (device)
+  const double* B = nullptr; int64_t ldb = 0;   // ldJ x M
+  int M = 0;
+  double coef = 0.0;
+};
+
+struct GOperator {
+  int64_t I = 0, ldI = 0, J = 0, ldJ = 0;
+  int64_t J_total = 0;     // over all ranks
+  const float* R = nullptr;
+  double c = 0.0;
+  int nterms = 0;
+  LowRankTerm t[2];
+};
+
+struct TsvdOpts {
+  int M = 0;
+  int extra = 12;       // block = M + extra
+  int depth = 3;        // Krylov extensions per cycle
+  double tol = 1e-4;    // Ritz residual estimate
+  int max_cycles = 40;  // restarts (cold start on gap-less spectra)
+  uint64_t seed = 0;
+  int variant = PROD_AUTO;
+};
+
+struct TsvdWs {
+  SmallWs small;
+  ProdWs prod;
+  DevBuf<double> Qb, Zb, Kb, tmpI, tmpJ, T, Tw, S, theta, C, est, Ub, Vb;
+  DevBuf<double> Vwarm;   // ldJ x b warm start for the next call
+  bool warm = false;
+  int b = 0;
+  int64_t passes_total = 0, calls = 0;
+};
+
+// outU: ldI x M, outD: M, outV: ldJ x M (device, column-major)
+void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* outU, double* outD,
+          double* outV, int* passes_out, double* est_out);
+
+}  // namespace scgbm
