@@ -138,6 +138,17 @@ typedef struct scgbm_fit_out {
 
 int scgbm_fit(const scgbm_fit_args* args, scgbm_fit_out* out);
 
+/* The same fit, driven trip by trip (R/fit.R:125-186 is one trip).  `begin` uploads Y
+ * and runs the setup + initial SVD (R/fit.R:76-123); `step` runs up to n_steps loop
+ * trips and sets *done when the loop has ended (break, or max.iter reached); `end`
+ * assembles the outputs (R/fit.R:188-210) and frees the handle (out may be NULL to
+ * just free).  An R shim uses this to call R_CheckUserInterrupt between trips. */
+typedef struct scgbm_fit_handle scgbm_fit_handle;
+int scgbm_fit_begin(const scgbm_fit_args* args, scgbm_fit_handle** handle);
+int scgbm_fit_step(scgbm_fit_handle* handle, int32_t n_steps, int32_t* done);
+int scgbm_fit_profile(scgbm_fit_handle* handle, scgbm_profile* prof); /* cumulative so far */
+int scgbm_fit_end(scgbm_fit_handle* handle, scgbm_fit_out* out);
+
 /* ---- get.se(out, EPS)   R/uncertainty.R:14-35 --------------------------------- */
 typedef struct scgbm_se_args {
   int64_t I, J;         /* J = this rank's cells                                    */

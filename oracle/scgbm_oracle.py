@@ -225,16 +225,26 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
 
 # ----------------------------------------------------------------------------
 def poisson_glm_irls(Xd, y, offset, tol=1e-8, maxit=100):
-    """fastglm(x, y, offset, family=poisson(), method=3) [ext]: IRLS, LLT solve.
-    Returns (coef, se, converged)."""
+    """fastglm(x, y, offset, family=poisson(), method=3) [ext]: IRLS with an LLT
+    solve per step; start mu = y + 0.1 (poisson()$initialize); stop when
+    |dev - devold| / (|dev| + 0.1) < tol; the standard errors come from the X'WX of
+    the LAST solve (the weights that produced the returned coefficients), as in
+    fastglm's save_se() and R's glm.fit/summary.glm.  Returns (coef, se, converged,
+    n_solves)."""
     n, p = Xd.shape
-    mu = y + 0.1                                   # poisson()$initialize
+    mu = y + 0.1
     eta = np.log(mu)
-    with np.errstate(divide="ignore", invalid="ignore"):
-        dev = 2.0 * np.sum(np.where(y > 0, y * np.log(y / mu), 0.0) - (y - mu))
+
+    def deviance(mu):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return 2.0 * np.sum(np.where(y > 0, y * np.log(y / mu), 0.0) - (y - mu))
+
+    dev = deviance(mu)
     coef = np.zeros(p)
+    A = None
     conv = False
-    for _ in range(maxit):
+    it = 0
+    for it in range(1, maxit + 1):
         w = mu                                     # (dmu/deta)^2 / var = mu
         z = (eta - offset) + (y - mu) / mu
         XtW = Xd.T * w
@@ -245,21 +255,18 @@ def poisson_glm_irls(Xd, y, offset, tol=1e-8, maxit=100):
         eta = Xd @ coef + offset
         mu = np.exp(eta)
         devold = dev
-        with np.errstate(divide="ignore", invalid="ignore"):
-            dev = 2.0 * np.sum(np.where(y > 0, y * np.log(y / mu), 0.0) - (y - mu))
+        dev = deviance(mu)
         if not np.isfinite(dev):
             raise FloatingPointError("non-finite deviance")
         if abs(dev - devold) / (abs(dev) + 0.1) < tol:
             conv = True
             break
-    XtW = Xd.T * mu
-    cov = np.linalg.inv(XtW @ Xd)
-    se = np.sqrt(np.diag(cov))
-    return coef, se, conv
+    se = np.sqrt(np.diag(np.linalg.inv(A)))
+    return coef, se, conv, it
 
 
 def gbm_proj_parallel(Y, M, subsample, ncores=1, tol=1e-4, max_iter=100, svd="exact",
-                      rng=None, verbose=False, glm_tol=1e-8):
+                      rng=None, verbose=False, glm_tol=1e-8, _subfit=None):
     """R/fit.R:213-285.  `subsample` scalar -> `rng.choice` (R's sample() stream is
     not restated); vector -> 1-based column indices as in R (:221-223)."""
     Y = np.asarray(Y, dtype=np.float64)
@@ -274,7 +281,10 @@ def gbm_proj_parallel(Y, M, subsample, ncores=1, tol=1e-4, max_iter=100, svd="ex
     Y_sub = Y[:, jxs]
     ixs = np.nonzero(Y_sub.sum(axis=1) > 5)[0]                         # :225
     Y_sub = Y_sub[ixs, :]
-    out = gbm_sc(Y_sub, M=M, tol=tol, max_iter=max_iter, svd=svd, rng=rng, verbose=verbose)  # :227
+    if _subfit is not None:      # test hook: reuse a given subsample fit (isolates the projection step)
+        out = dict(_subfit)
+    else:
+        out = gbm_sc(Y_sub, M=M, tol=tol, max_iter=max_iter, svd=svd, rng=rng, verbose=verbose)  # :227
     U = np.hstack([np.ones((len(ixs), 1)), out["U"]])                  # :229-232
     alpha = out["alpha"][:, 0]                                         # :234
     Yf = Y[ixs, :]                                                     # :237
@@ -282,7 +292,7 @@ def gbm_proj_parallel(Y, M, subsample, ncores=1, tol=1e-4, max_iter=100, svd="ex
     fail = np.zeros(J, dtype=bool)
     for j in range(J):                                                 # :248-264
         try:
-            coef, se, _ = poisson_glm_irls(U, Yf[:, j], alpha, tol=glm_tol)
+            coef, se, _, _ = poisson_glm_irls(U, Yf[:, j], alpha, tol=glm_tol)
             V[j, : M + 1] = coef
             V[j, M + 1:] = se[1:]
         except Exception:                                              # try({...}) :251

@@ -11,6 +11,11 @@ Comm* comm_create(const uint8_t* id, int nranks, int rank, int device);
 void comm_unique_id(uint8_t* id);
 void comm_destroy(Comm* c);
 void fit_impl(const scgbm_fit_args* a, scgbm_fit_out* out);
+struct FitRun;
+FitRun* fit_begin_impl(const scgbm_fit_args* a);
+int fit_step_impl(FitRun* r, int n_steps);
+void fit_profile_impl(FitRun* r, scgbm_profile* p);
+void fit_end_impl(FitRun* r, scgbm_fit_out* out);
 void get_se_impl(const scgbm_se_args* a, scgbm_se_out* out);
 void project_impl(const scgbm_proj_args* a, scgbm_proj_out* out);
 void sim_counts(const scgbm_sim_args* a, void* Y_dev, int64_t* n_saturated);
@@ -50,6 +55,18 @@ static void use_device(int device) {
 extern "C" {
 
 int scgbm_fit(const scgbm_fit_args* args, scgbm_fit_out* out) { return guarded([&] { fit_impl(args, out); }); }
+int scgbm_fit_begin(const scgbm_fit_args* args, scgbm_fit_handle** h) {
+  return guarded([&] { SCGBM_REQUIRE(h, "NULL handle pointer"); *h = reinterpret_cast<scgbm_fit_handle*>(fit_begin_impl(args)); });
+}
+int scgbm_fit_step(scgbm_fit_handle* h, int32_t n_steps, int32_t* done) {
+  return guarded([&] { const int d = fit_step_impl(reinterpret_cast<FitRun*>(h), n_steps); if (done) *done = d; });
+}
+int scgbm_fit_profile(scgbm_fit_handle* h, scgbm_profile* prof) {
+  return guarded([&] { fit_profile_impl(reinterpret_cast<FitRun*>(h), prof); });
+}
+int scgbm_fit_end(scgbm_fit_handle* h, scgbm_fit_out* out) {
+  return guarded([&] { fit_end_impl(reinterpret_cast<FitRun*>(h), out); });
+}
 int scgbm_get_se(const scgbm_se_args* args, scgbm_se_out* out) { return guarded([&] { get_se_impl(args, out); }); }
 int scgbm_project(const scgbm_proj_args* args, scgbm_proj_out* out) { return guarded([&] { project_impl(args, out); }); }
 int scgbm_sim_counts(const scgbm_sim_args* args, void* Y_dev, int64_t* n_saturated) {

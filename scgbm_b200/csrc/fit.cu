@@ -339,36 +339,56 @@ static double now_sec() {
   return duration<double>(steady_clock::now().time_since_epoch()).count();
 }
 
-void fit_impl(const scgbm_fit_args* a, scgbm_fit_out* out) {
-  SCGBM_REQUIRE(a && out, "NULL args");
-  SCGBM_REQUIRE(a->I >= 1 && a->J >= 1, "Y must be a non-empty matrix");
-  SCGBM_REQUIRE(a->M >= 1, "M must be >= 1");
-  SCGBM_REQUIRE(a->max_iter >= 1, "max.iter must be >= 1");
-  SCGBM_REQUIRE(out->U && out->D && out->V && out->alpha && out->beta && out->obj, "output buffers missing");
-  Ctx ctx(a->device, reinterpret_cast<Comm*>(a->comm));
-  ctx.prof.timing = a->profile != 0;
-  cudaEvent_t ev0, ev1;
-  SCGBM_CUDA(cudaEventCreate(&ev0));
-  SCGBM_CUDA(cudaEventCreate(&ev1));
-  SCGBM_CUDA(cudaEventRecord(ev0, ctx.stream));
-
-  FitState st(ctx, *a);
-  st.setup();
-  st.init_svd();
-  const int64_t I = st.I, J = st.J, ldI = st.ldI, ldJ = st.ldJ;
-  const int M = st.M, nbatch = st.nbatch;
-  const int max_iter = a->max_iter;
-
-  std::vector<double> LL(max_iter, 0.0);
+// One fit in flight: scgbm_fit_begin / _step / _end drive it; scgbm_fit = all three.
+struct FitRun {
+  scgbm_fit_args a;
+  Ctx ctx;
+  FitState st;
+  std::vector<double> LL, obj, tvec;
+  std::vector<int8_t> acc;
   double lr = 1.0;                                       // R/fit.R:84
   int cur = 0, prev = -1, last = -1;                     // factor slots; prev == -1: Xt = 0 (R/fit.R:123)
-  int n_obj = 0, n_iter = 0, hit_max = 0;
-  double t_prev = now_sec(), t_cum = 0.0;
-  Factor zero_factor;
-  double fused_bytes = 0.0;
+  int i = 0;                                             // loop index of the last trip
+  int n_iter = 0, hit_max = 0;
+  bool finished = false;
+  double t_prev = 0, t_cum = 0, fused_bytes = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
-  for (int i = 1; i <= max_iter; ++i) {                  // R/fit.R:125
+  explicit FitRun(const scgbm_fit_args& args)
+      : a(args), ctx(args.device, reinterpret_cast<Comm*>(args.comm)), st(ctx, a) {
+    ctx.prof.timing = a.profile != 0;
+    SCGBM_CUDA(cudaEventCreate(&ev0));
+    SCGBM_CUDA(cudaEventCreate(&ev1));
+    SCGBM_CUDA(cudaEventRecord(ev0, ctx.stream));
+    st.setup();
+    st.init_svd();
+    LL.assign(a.max_iter, 0.0);
+    acc.assign(a.max_iter, 0);
+    tvec.assign(a.max_iter, 0.0);
+    t_prev = now_sec();
+    ctx.sync();
+  }
+  ~FitRun() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  }
+
+  void revert() {                                        // X <- Xt
+    if (prev >= 0) { cur = prev; return; }
+    int z = 0;                                           // Xt is still the zero matrix (R/fit.R:123)
+    while (z == cur) ++z;
+    st.slot[z].kind = XK_ZERO; st.slot[z].M = st.M;
+    cur = z;
+  }
+
+  // one trip through R/fit.R:125-186; returns false when the loop has ended
+  bool step() {
+    if (finished) return false;
+    if (i >= a.max_iter) { finished = true; return false; }
+    ++i;
     n_iter = i;
+    const int64_t I = st.I, J = st.J, ldI = st.ldI, ldJ = st.ldJ;
+    const int M = st.M, nbatch = st.nbatch;
     const Factor& fc = st.slot[cur];
     const XDesc xc = st.desc(fc);
     // (a) alphas <- log.rsy - log(rowSums(exp(X + betas)))      R/fit.R:127-130
@@ -383,7 +403,7 @@ void fit_impl(const scgbm_fit_args* a, scgbm_fit_out* out) {
       SCGBM_LAUNCH_CHECK();
     }
     st.stage_rows();
-    if (a->infer_beta) {                                 // R/fit.R:133-135
+    if (a.infer_beta) {                                  // R/fit.R:133-135
       pass_colsum(ctx, st.eta, st.geom, xc, st.f_row.get(), st.Ccol.get());
       ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
       beta_infer_kernel<<<GRID1(J)>>>(J, st.logcs.get(), st.Ccol.get(), st.beta.get());
@@ -402,44 +422,39 @@ void fit_impl(const scgbm_fit_args* a, scgbm_fit_out* out) {
     double h[3];
     SCGBM_CUDA(cudaMemcpyAsync(h, st.scal.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
     ctx.sync();
-    if (a->time_by_iter && out->time) {                  // R/fit.R:139-142
+    {                                                    // R/fit.R:139-142
       const double t = now_sec();
       t_cum += t - t_prev; t_prev = t;
-      out->time[i - 1] = t_cum;
+      tvec[i - 1] = t_cum;
     }
     const double ll = h[1] - h[0];                       // R/fit.R:151
     const double w_max = h[2];
     LL[i - 1] = ll;
-    if (out->LL) out->LL[i - 1] = ll;
-    if (out->accepted) out->accepted[i - 1] = 0;
-    if (a->verbose) fprintf(stderr, "[scgbm] iter %d LL=%.10g lr=%.4g wmax=%.6g\n", i, ll, lr, w_max);
+    acc[i - 1] = 0;
+    if (a.verbose) fprintf(stderr, "[scgbm] iter %d LL=%.10g lr=%.4g wmax=%.6g\n", i, ll, lr, w_max);
 
     if (std::isnan(ll) || std::isinf(ll)) {              // R/fit.R:152-157
-      if (prev >= 0) cur = prev; else { cur = -2; }      // X <- Xt
+      revert();
       lr = lr / 2;
-      if (cur == -2) {                                   // Xt is the zero matrix (only before the first accept)
-        st.slot[2].kind = XK_ZERO; st.slot[2].M = M; cur = 2;
-      }
-      continue;
+      return true;
     }
     if (i >= 3) {                                        // R/fit.R:158
       const double tau = std::fabs((ll - LL[i - 3]) / ll);
-      if (tau < a->tol && lr <= 1.06 && i >= a->min_iter) break;        // R/fit.R:160-162
+      if (tau < a.tol && lr <= 1.06 && i >= a.min_iter) { finished = true; return false; }   // R/fit.R:160-162
       const double llp = LL[i - 2];
       if (std::isnan(llp))                               // quirk Q1: if (NA) errors in R
         throw Error(SCGBM_ERR_NUMERIC, "missing value where TRUE/FALSE needed (objective was NaN at the previous iteration)");
       if (ll < llp) {                                    // R/fit.R:164-167
         lr = std::max(lr / 2, 1.0);
-        if (prev >= 0) cur = prev;
-        else { st.slot[2].kind = XK_ZERO; st.slot[2].M = M; cur = 2; }
-        continue;
+        revert();
+        return true;
       } else {
         lr = lr * 1.05;                                  // R/fit.R:169
       }
     }
-    out->obj[n_obj++] = ll;                              // R/fit.R:174
-    if (out->accepted) out->accepted[i - 1] = 1;
-    if (a->progress) a->progress(i, ll, a->progress_user);   // R/fit.R:175
+    obj.push_back(ll);                                   // R/fit.R:174
+    acc[i - 1] = 1;
+    if (a.progress) a.progress(i, ll, a.progress_user);  // R/fit.R:175
 
     // (k) pgd_irlba                                               R/fit.R:315-328
     const double m = (double)(i - 1) / (double)(i + 2);  // R/fit.R:319
@@ -468,73 +483,130 @@ void fit_impl(const scgbm_fit_args* a, scgbm_fit_out* out) {
     tsvd(ctx, st.svd, op, o, fn.U.get(), fn.d.get(), fn.V.get(), nullptr, nullptr);   // R/fit.R:323
     st.stage_factor(fn);                                 // X <- u d v^T (never materialised; R/fit.R:324)
     prev = cur; cur = next; last = next;                 // R/fit.R:179-180,320
-    if (i == max_iter) hit_max = 1;                      // R/fit.R:182-185
+    if (i == a.max_iter) { hit_max = 1; finished = true; return false; }   // R/fit.R:182-185
+    return true;
   }
-  if (last < 0)
-    throw Error(SCGBM_ERR_NUMERIC, "no projected-gradient step was taken (object 'pgd' not found in the reference)");
+
+  void fill_profile(scgbm_profile* p) {
+    SCGBM_CUDA(cudaEventRecord(ev1, ctx.stream));
+    ctx.sync();
+    float tot = 0;
+    cudaEventElapsedTime(&tot, ev0, ev1);
+    memset(p, 0, sizeof(*p));
+    ctx.prof.fill(p);
+    p->total_ms = tot;
+    p->fused_bytes = fused_bytes;
+    p->svd_passes = st.svd.passes_total;
+    p->svd_calls = st.svd.calls;
+  }
 
   // ---- assemble (R/fit.R:188-204, 301-313) -------------------------------------
-  out->n_obj = n_obj; out->n_iter = n_iter; out->hit_max_iter = hit_max;
-  out->y_storage = st.Y.storage; out->max_Y = st.maxY;
-  const Factor& fl = st.slot[last];
-  std::vector<double> hU((size_t)ldI * M), hV((size_t)ldJ * M), hD(M), hA((size_t)ldI * nbatch), hB(ldJ);
-  SCGBM_CUDA(cudaMemcpyAsync(hU.data(), fl.U.get(), hU.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
-  SCGBM_CUDA(cudaMemcpyAsync(hV.data(), fl.V.get(), hV.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
-  SCGBM_CUDA(cudaMemcpyAsync(hD.data(), fl.d.get(), M * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
-  SCGBM_CUDA(cudaMemcpyAsync(hA.data(), st.alpha.get(), hA.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
-  SCGBM_CUDA(cudaMemcpyAsync(hB.data(), st.beta.get(), hB.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
-  ctx.sync();
-  ctx.prof.d2h_bytes += (double)(hU.size() + hV.size() + hA.size() + hB.size()) * sizeof(double);
-  // sign convention: the FIRST gene of the GLOBAL matrix decides; U is replicated so every rank agrees
-  for (int m2 = 0; m2 < M; ++m2) {
-    const bool flip = hU[(size_t)m2 * ldI + 0] < 0;                       // R/fit.R:305
-    for (int64_t i2 = 0; i2 < I; ++i2) {
-      const double u = hU[(size_t)m2 * ldI + i2];
-      if (out->loadings) out->loadings[(size_t)m2 * I + i2] = u;          // pre-flip (Q7, R/fit.R:196)
-      out->U[(size_t)m2 * I + i2] = flip ? -u : u;
+  void finish(scgbm_fit_out* out) {
+    SCGBM_REQUIRE(out && out->U && out->D && out->V && out->alpha && out->beta && out->obj, "output buffers missing");
+    if (last < 0)
+      throw Error(SCGBM_ERR_NUMERIC, "no projected-gradient step was taken (object 'pgd' not found in the reference)");
+    const int64_t I = st.I, J = st.J, ldI = st.ldI, ldJ = st.ldJ;
+    const int M = st.M, nbatch = st.nbatch;
+    out->n_obj = (int)obj.size(); out->n_iter = n_iter; out->hit_max_iter = hit_max;
+    out->y_storage = st.Y.storage; out->max_Y = st.maxY;
+    for (size_t k = 0; k < obj.size(); ++k) out->obj[k] = obj[k];
+    for (int k = 0; k < n_iter; ++k) {
+      if (out->LL) out->LL[k] = LL[k];
+      if (out->accepted) out->accepted[k] = acc[k];
+      if (out->time && a.time_by_iter) out->time[k] = tvec[k];
     }
-    for (int64_t j2 = 0; j2 < J; ++j2) {
-      const double v = hV[(size_t)m2 * ldJ + j2];
-      const double vf = flip ? -v : v;
-      out->V[(size_t)m2 * J + j2] = vf;
-      if (out->scores) out->scores[(size_t)m2 * J + j2] = vf * hD[m2];    // R/fit.R:310
-    }
-    out->D[m2] = hD[m2];
-  }
-  for (int k = 0; k < nbatch; ++k)
-    for (int64_t i2 = 0; i2 < I; ++i2) out->alpha[(size_t)k * I + i2] = hA[(size_t)k * ldI + i2];
-  for (int64_t j2 = 0; j2 < J; ++j2) out->beta[j2] = hB[j2];
-
-  if (a->return_W && out->W) {                           // R/fit.R:189-191 (unclipped, current X)
-    const Factor& fc = st.slot[cur];
-    int64_t jc_max = std::max<int64_t>(1, (int64_t)(64ll << 20) / I);
-    jc_max = std::min(jc_max, J);
-    DevBuf<double> Wd(I * jc_max);
-    for (int64_t j0 = 0; j0 < J; j0 += jc_max) {
-      const int64_t jc = std::min(jc_max, J - j0);
-      {
-        ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
-        write_w_kernel<<<GRID1(I * jc)>>>(I, ldI, j0, jc, ldJ, fc.M, fc.kind, fc.U.get(), fc.d.get(), fc.V.get(),
-                                          st.alpha.get(), st.beta.get(), st.Y.batch.get(), st.alpha0.get(),
-                                          st.beta0.get(), Wd.get());
-        SCGBM_LAUNCH_CHECK();
+    const Factor& fl = st.slot[last];
+    std::vector<double> hU((size_t)ldI * M), hV((size_t)ldJ * M), hD(M), hA((size_t)ldI * nbatch), hB(ldJ);
+    SCGBM_CUDA(cudaMemcpyAsync(hU.data(), fl.U.get(), hU.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    SCGBM_CUDA(cudaMemcpyAsync(hV.data(), fl.V.get(), hV.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    SCGBM_CUDA(cudaMemcpyAsync(hD.data(), fl.d.get(), M * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    SCGBM_CUDA(cudaMemcpyAsync(hA.data(), st.alpha.get(), hA.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    SCGBM_CUDA(cudaMemcpyAsync(hB.data(), st.beta.get(), hB.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+    ctx.prof.d2h_bytes += (double)(hU.size() + hV.size() + hA.size() + hB.size()) * sizeof(double);
+    // sign convention: gene 1 decides (U is replicated, so every rank flips alike)
+    for (int m2 = 0; m2 < M; ++m2) {
+      const bool flip = hU[(size_t)m2 * ldI + 0] < 0;                       // R/fit.R:305
+      for (int64_t i2 = 0; i2 < I; ++i2) {
+        const double u = hU[(size_t)m2 * ldI + i2];
+        if (out->loadings) out->loadings[(size_t)m2 * I + i2] = u;          // pre-flip (Q7, R/fit.R:196)
+        out->U[(size_t)m2 * I + i2] = flip ? -u : u;
       }
-      SCGBM_CUDA(cudaMemcpyAsync(out->W + j0 * I, Wd.get(), I * jc * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
-      ctx.sync();
-      ctx.prof.d2h_bytes += (double)I * jc * sizeof(double);
+      for (int64_t j2 = 0; j2 < J; ++j2) {
+        const double v = hV[(size_t)m2 * ldJ + j2];
+        const double vf = flip ? -v : v;
+        out->V[(size_t)m2 * J + j2] = vf;
+        if (out->scores) out->scores[(size_t)m2 * J + j2] = vf * hD[m2];    // R/fit.R:310
+      }
+      out->D[m2] = hD[m2];
     }
+    for (int k = 0; k < nbatch; ++k)
+      for (int64_t i2 = 0; i2 < I; ++i2) out->alpha[(size_t)k * I + i2] = hA[(size_t)k * ldI + i2];
+    for (int64_t j2 = 0; j2 < J; ++j2) out->beta[j2] = hB[j2];
+
+    if (a.return_W && out->W) {                          // R/fit.R:189-191 (unclipped, current X)
+      const Factor& fc = st.slot[cur];
+      int64_t jc_max = std::max<int64_t>(1, (int64_t)(64ll << 20) / I);
+      jc_max = std::min(jc_max, J);
+      DevBuf<double> Wd(I * jc_max);
+      for (int64_t j0 = 0; j0 < J; j0 += jc_max) {
+        const int64_t jc = std::min(jc_max, J - j0);
+        {
+          ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
+          write_w_kernel<<<GRID1(I * jc)>>>(I, ldI, j0, jc, ldJ, fc.M, fc.kind, fc.U.get(), fc.d.get(), fc.V.get(),
+                                            st.alpha.get(), st.beta.get(), st.Y.batch.get(), st.alpha0.get(),
+                                            st.beta0.get(), Wd.get());
+          SCGBM_LAUNCH_CHECK();
+        }
+        SCGBM_CUDA(cudaMemcpyAsync(out->W + j0 * I, Wd.get(), I * jc * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+        ctx.sync();
+        ctx.prof.d2h_bytes += (double)I * jc * sizeof(double);
+      }
+    }
+    fill_profile(&out->prof);
   }
-  SCGBM_CUDA(cudaEventRecord(ev1, ctx.stream));
-  ctx.sync();
-  float tot = 0;
-  cudaEventElapsedTime(&tot, ev0, ev1);
-  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
-  memset(&out->prof, 0, sizeof(out->prof));
-  ctx.prof.fill(&out->prof);
-  out->prof.total_ms = tot;
-  out->prof.fused_bytes = fused_bytes;
-  out->prof.svd_passes = st.svd.passes_total;
-  out->prof.svd_calls = st.svd.calls;
+};
+
+static void check_fit_args(const scgbm_fit_args* a) {
+  SCGBM_REQUIRE(a, "NULL args");
+  SCGBM_REQUIRE(a->I >= 1 && a->J >= 1, "Y must be a non-empty matrix");
+  SCGBM_REQUIRE(a->M >= 1, "M must be >= 1");
+  SCGBM_REQUIRE(a->max_iter >= 1, "max.iter must be >= 1");
+}
+
+FitRun* fit_begin_impl(const scgbm_fit_args* a) {
+  check_fit_args(a);
+  return new FitRun(*a);
+}
+int fit_step_impl(FitRun* r, int n_steps) {
+  SCGBM_REQUIRE(r, "NULL handle");
+  SCGBM_CUDA(cudaSetDevice(r->ctx.device));
+  for (int k = 0; k < n_steps; ++k)
+    if (!r->step()) return 1;
+  return r->finished ? 1 : 0;
+}
+void fit_profile_impl(FitRun* r, scgbm_profile* p) {
+  SCGBM_REQUIRE(r && p, "NULL handle");
+  SCGBM_CUDA(cudaSetDevice(r->ctx.device));
+  r->fill_profile(p);
+}
+void fit_end_impl(FitRun* r, scgbm_fit_out* out) {
+  SCGBM_REQUIRE(r, "NULL handle");
+  SCGBM_CUDA(cudaSetDevice(r->ctx.device));
+  try {
+    if (out) r->finish(out);
+  } catch (...) { delete r; throw; }
+  delete r;
+}
+void fit_impl(const scgbm_fit_args* a, scgbm_fit_out* out) {
+  check_fit_args(a);
+  SCGBM_REQUIRE(out && out->U && out->D && out->V && out->alpha && out->beta && out->obj, "output buffers missing");
+  FitRun* r = new FitRun(*a);
+  try {
+    while (r->step()) {}
+    r->finish(out);
+  } catch (...) { delete r; throw; }
+  delete r;
 }
 
 }  // namespace scgbm

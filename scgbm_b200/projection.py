@@ -1,0 +1,63 @@
+"""gbm.proj.parallel (R/fit.R:213-285): fit on a subsample of cells, then project
+every cell onto the fitted loadings with one Poisson GLM per cell.  The subsample
+draw, row filter and re-centring stay on the host like the reference's R code; the
+fit and the J per-cell GLMs run on the GPU (scgbm_fit, scgbm_project)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def gbm_proj_parallel(Y, M, subsample=2000, min_counts=5, ncores=1, tol=1e-4, max_iter=100, *,
+                      device=-1, rng=None, profile=False, svd_tol=0.0, seed=0, glm_tol=1e-8, glm_maxit=100):
+    from .api import gbm_sc, _as_counts
+    lib = L.load()
+    Yh, y_dt = _as_counts(Y)
+    I, J = Yh.shape
+    rs = Yh.sum(axis=1, dtype=np.float64)
+    with np.errstate(divide="ignore"):
+        alphas_full = np.log(rs)                                           # R/fit.R:217
+    if np.ndim(subsample) == 0:                                            # R/fit.R:218-220
+        rng = rng or np.random.default_rng()
+        jxs = rng.choice(J, size=int(subsample), replace=False)            # sample(1:J, size)
+    else:
+        jxs = np.asarray(subsample, dtype=np.int64) - 1                    # 1-based like R (:221-223)
+    Y_sub = np.asfortranarray(Yh[:, jxs])                                  # as.matrix(Y.sub)  :224
+    ixs = np.nonzero(Y_sub.sum(axis=1, dtype=np.float64) > 5)[0]           # hard-coded 5  :225
+    Y_sub = np.asfortranarray(Y_sub[ixs, :])
+    out = gbm_sc(Y_sub, M, tol=tol, max_iter=max_iter, device=device, profile=profile,
+                 diagnostics=profile, svd_tol=svd_tol, seed=seed)          # :227
+    Uk = np.asfortranarray(out["U"])                                       # :229
+    alpha_k = np.ascontiguousarray(out["alpha"][:, 0])                     # :234
+    ixs64 = np.ascontiguousarray(ixs.astype(np.int64))
+    beta = np.zeros(J); scores = np.zeros((J, M), order="F"); se_scores = np.zeros((J, M), order="F")
+    fail = np.zeros(J, dtype=np.int8); iters = np.zeros(J, dtype=np.int32)
+    a = L.ProjArgs()
+    a.Y = L.ptr(Yh); a.y_dtype = y_dt; a.y_on_device = 0; a.I_full = I; a.J = J; a.ldY = I
+    a.ixs = L.ptr(ixs64); a.Ik = len(ixs64); a.M = int(M); a.U = L.ptr(Uk); a.alpha = L.ptr(alpha_k)
+    a.glm_tol = float(glm_tol); a.glm_maxit = int(glm_maxit); a.device = int(device); a.profile = int(bool(profile))
+    o = L.ProjOut()
+    o.beta = L.ptr(beta); o.scores = L.ptr(scores); o.se_scores = L.ptr(se_scores)
+    o.fail = L.ptr(fail); o.iters = L.ptr(iters)
+    L.check(lib.scgbm_project(C.byref(a), C.byref(o)))
+    out["se_scores"] = se_scores                                           # :268
+    out["scores"] = scores                                                 # :269
+    alpha = np.zeros(I)                                                    # :272
+    alpha[ixs] = out["alpha"][:, 0]                                        # :273
+    mask = np.ones(I, dtype=bool); mask[ixs] = False
+    with np.errstate(over="ignore"):
+        alpha[mask] = alphas_full[mask] - np.log(np.exp(beta).sum())       # :274
+    am = alpha.mean()
+    out["beta"] = beta + am                                                # :275
+    out["alpha"] = alpha - am                                              # :276-277
+    Uf = np.zeros((I, M), order="F"); Uf[ixs, :] = out["U"]                # :278-280
+    out["U"] = Uf
+    out["V"] = None                                                        # :281
+    out["loadings"] = None   # :282 assigns the undefined `loadings` (stats::loadings): a reference bug
+    out["_ixs"] = ixs; out["_jxs"] = jxs; out["_fail"] = fail.astype(bool); out["_glm_iters"] = iters
+    if profile:
+        out["_prof_proj"] = o.prof.as_dict()
+    return out
