@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: gbm.sc outer-loop iterations/second (and fit
+seconds) at 20k genes x 1M cells, M = 20, on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: under torchrun)
+    python bench.py --impl reference ...                      (CPU arm, rank 0 only)
+
+A "step" is one trip through the loop body of R/fit.R:125-186 over the whole count
+matrix (alpha update, fused likelihood pass, accept/revert control, truncated SVD).
+`value`   : K steps / device time, Y already resident in HBM (u16), max over ranks.
+`e2e`     : a complete default gbm.sc(Y, M) call through the public API with HOST
+            (pinned, int32 = R integer) buffers: H2D of Y, setup, initial SVD, all
+            iterations and the D2H of the results are inside the timed region.
+`roofline`: the fused likelihood pass (K4) -- algorithmic bytes / mean launch time.
+`cpu_baseline`: the float64 oracle (numpy/scipy restatement of R/fit.R, NOT R) on a
+            bounded slice of the same synthetic matrix, extrapolated linearly in I*J.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------
+# synthetic workload: simData recipe (R/simulate.R:24-48), ~90 % zeros
+# ----------------------------------------------------------------------------------
+def zero_fraction(mu_total, sd2=2.0):
+    """P(Y = 0) for Y ~ Poisson(exp(z)), z ~ N(mu_total, sd2) (alpha + beta)."""
+    x, w = np.polynomial.hermite_e.hermegauss(80)
+    z = mu_total + math.sqrt(sd2) * x
+    return float(np.sum(w * np.exp(-np.exp(z))) / np.sum(w))
+
+
+def solve_mean_for_zeros(target=0.90):
+    lo, hi = -10.0, 3.0
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        if zero_fraction(mid) > target:
+            lo = mid
+        else:
+            hi = mid
+    return 0.5 * (lo + hi)
+
+
+class Workload:
+    def __init__(self, I, J, d, seed=1, zeros=0.90):
+        self.I, self.J, self.d, self.seed = I, J, d, seed
+        rng = np.random.default_rng(seed)
+        U, _ = np.linalg.qr(rng.standard_normal((I, d)))
+        V, _ = np.linalg.qr(rng.standard_normal((J, d)))
+        for m in range(d):
+            if U[0, m] < 0:
+                U[:, m] = -U[:, m]; V[:, m] = -V[:, m]
+        self.U = np.asfortranarray(U); self.V = V
+        self.D = np.linspace(2 * (math.sqrt(I) + math.sqrt(J)), math.sqrt(I) + math.sqrt(J), d)
+        mu = solve_mean_for_zeros(zeros)
+        self.alpha = rng.normal(mu / 2, 1.0, I)
+        self.beta = rng.normal(mu / 2, 1.0, J)
+        self.mu_total = mu
+
+    def sim_into(self, lib, L, dev_ptr, j0, j1, ld, out_dtype, device):
+        a = L.SimArgs()
+        Vl = np.asfortranarray(self.V[j0:j1]); bl = np.ascontiguousarray(self.beta[j0:j1])
+        a.I = self.I; a.J = j1 - j0; a.ld = ld; a.j_offset = j0; a.d = self.d
+        a.U = L.ptr(self.U); a.V = L.ptr(Vl); a.D = L.ptr(self.D); a.alpha = L.ptr(self.alpha); a.beta = L.ptr(bl)
+        a.nb_theta = 0.0; a.seed = self.seed; a.out_dtype = out_dtype; a.device = device
+        nsat = C.c_int64(0)
+        L.check(lib.scgbm_sim_counts(C.byref(a), dev_ptr, C.byref(nsat)))
+        return nsat.value
+
+    def host_slice(self, lib, L, j0, j1, device, rows=None):
+        """int32 host copy of columns [j0, j1) (optionally the first `rows` genes)."""
+        I = self.I
+        n = j1 - j0
+        p = C.c_void_p()
+        L.check(lib.scgbm_dev_alloc(C.byref(p), I * n * 4, device))
+        try:
+            self.sim_into(lib, L, p, j0, j1, I, L.I32, device)
+            Y = np.empty((I, n), dtype=np.int32, order="F")
+            L.check(lib.scgbm_memcpy_d2h(L.ptr(Y), p, I * n * 4, device))
+        finally:
+            lib.scgbm_dev_free(p, device)
+        return Y if rows is None else np.asfortranarray(Y[:rows])
+
+
+# ----------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi style clocks line sampled DURING the timed region (pynvml)."""
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.samples, self.reasons, self.max_mhz = device, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            log("pynvml unavailable:", e)
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(2.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(wl, M, steps, warmup, sample_cells):
+    """oracle (numpy/scipy float64 restatement, svds as the irlba stand-in) on a bounded slice
+    of the same synthetic model (first `sample_cells` cells, all genes), generated on the host."""
+    from oracle import scgbm_oracle as O
+    rng = np.random.default_rng(wl.seed + 12345)
+    n = min(sample_cells, wl.J)
+    lam = np.exp(wl.alpha[:, None] + wl.beta[None, :n] + (wl.U * wl.D) @ wl.V[:n].T)
+    Ys = rng.poisson(lam).astype(np.int32)
+    del lam
+    keep_i = Ys.sum(1) > 0; keep_j = Ys.sum(0) > 0
+    Ys = Ys[keep_i][:, keep_j]
+    t0 = time.perf_counter()
+    out = O.gbm_sc(Ys, M, max_iter=warmup + steps, min_iter=10 ** 6, svd="svds", time_by_iter=True,
+                   rng=np.random.default_rng(0))
+    wall = time.perf_counter() - t0
+    t = np.asarray(out["time"])              # cumulative, sampled mid-iteration (R/fit.R:139-142)
+    per_iter = np.diff(t)[-max(1, steps - 1):] if len(t) > 2 else np.array([wall / max(1, len(t))])
+    sec_iter = float(np.mean(per_iter))
+    scale = (Ys.shape[0] * Ys.shape[1]) / (wl.I * wl.J)
+    try:
+        from threadpoolctl import threadpool_info
+        blas = ", ".join(sorted({f"{i.get('internal_api')} {i.get('version')} x{i.get('num_threads')}" for i in threadpool_info()}))
+    except Exception:
+        blas = "unknown"
+    return {
+        "value": scale / sec_iter, "unit": "iters/s", "cores": os.cpu_count(), "kind": "port",
+        "sample": f"oracle (float64 numpy/scipy restatement of R/fit.R, svds tol=1e-5 for irlba; NOT R) on "
+                  f"{Ys.shape[0]}x{Ys.shape[1]} of the {wl.I}x{wl.J} matrix, M={M}, {len(t)} iterations, "
+                  f"{sec_iter:.3f} s/iter measured, extrapolated linearly in I*J (x{1 / scale:.0f}); BLAS: {blas}",
+        "sec_per_iter_sample": sec_iter, "sample_shape": [int(Ys.shape[0]), int(Ys.shape[1])], "wall_s": wall,
+    }
+
+
+# ----------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genes", type=int, default=int(os.environ.get("SCGBM_BENCH_GENES", 20000)))
+    ap.add_argument("--cells", type=int, default=int(os.environ.get("SCGBM_BENCH_CELLS", 1000000)))
+    ap.add_argument("--factors", type=int, default=20)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-max-iter", type=int, default=100)
+    ap.add_argument("--cpu-sample-cells", type=int, default=2000)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    I, J, M = args.genes, args.cells, args.factors
+    K, W = args.steps, max(args.warmup, 0)
+    workload = f"{I}x{J} Poisson simData-recipe counts (d={M}, ~90% zeros), gbm.sc(Y, M={M})"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        wl = Workload(I, J, M)
+        cb = cpu_baseline(wl, M, K, W, args.cpu_sample_cells)
+        line = {"impl": "reference", "metric": "gbm_sc_iters_per_sec", "value": cb["value"], "unit": "iters/s",
+                "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1000.0 / cb["value"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload}, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    from scgbm_b200 import _lib as L, gbm_sc
+    from scgbm_b200.dist import shard_range, init_comm, torch_broadcast_bytes
+    lib = L.load()
+    device = local_rank
+    comm = None
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        comm = init_comm(rank, world, device, torch_broadcast_bytes())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    t_gen = time.perf_counter()
+    wl = Workload(I, J, M)
+    j0, j1 = shard_range(J, rank, world)
+    Jl = j1 - j0
+    ldI = (I + 63) // 64 * 64
+    ydev = C.c_void_p()
+    L.check(lib.scgbm_dev_alloc(C.byref(ydev), ldI * Jl * 2, device))
+    nsat = wl.sim_into(lib, L, ydev, j0, j1, ldI, L.U16, device)
+    log(f"rank {rank}: generated {I}x{Jl} u16 counts on device in {time.perf_counter() - t_gen:.1f}s, saturated={nsat}")
+
+    # ---------------- value: K steps with Y resident in HBM ----------------------
+    a = L.FitArgs()
+    a.Y = ydev; a.y_dtype = L.U16; a.y_on_device = 1; a.I = I; a.J = Jl; a.ldY = ldI
+    a.M = M; a.max_iter = W + K + 1; a.tol = 1e-4; a.min_iter = 10 ** 6; a.infer_beta = 0
+    a.batch = None; a.nbatch = 1; a.return_W = 0; a.time_by_iter = 0
+    a.y_storage = L.STORE_U16; a.device = device; a.comm = comm.handle if comm else None
+    a.profile = 1; a.seed = 0
+    h = C.c_void_p()
+    t0 = time.perf_counter()
+    L.check(lib.scgbm_fit_begin(C.byref(a), C.byref(h)))
+    log(f"rank {rank}: setup + initial SVD {time.perf_counter() - t0:.2f}s")
+    done = C.c_int32(0)
+    if W > 0:
+        L.check(lib.scgbm_fit_step(h, W, C.byref(done)))
+    p0 = L.Profile(); p1 = L.Profile()
+    sampler = ClockSampler(device)                          # nvmlInit happens here, outside the timed region
+    barrier()
+    sampler.start()
+    L.check(lib.scgbm_fit_profile(h, C.byref(p0)))          # records an event on the launch stream + sync
+    L.check(lib.scgbm_fit_step(h, K, C.byref(done)))
+    L.check(lib.scgbm_fit_profile(h, C.byref(p1)))
+    clocks = sampler.stop()
+    barrier()
+    ms = max_over_ranks(p1.total_ms - p0.total_ms)
+    d0, d1 = p0.as_dict(), p1.as_dict()
+    launches = {k: d1["launches"][k] - d0["launches"][k] for k in d1["launches"]}
+    kms = {k: d1["ms"][k] - d0["ms"][k] for k in d1["ms"]}
+    fused_ms = kms["fused"] / max(1, launches["fused"])
+    fused_bytes = d1["fused_bytes"]
+    svd_passes = d1["svd_passes"] - d0["svd_passes"]
+    L.check(lib.scgbm_fit_end(h, None))
+    peak, peak_src = measured_peak()
+    achieved = fused_bytes / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "fused_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "kernel": "eta_rows_kernel<MODE_FUSED> (K4 fused likelihood pass)", "peak_source": peak_src,
+                "bytes_per_launch": fused_bytes, "ms_per_launch": fused_ms,
+                "note": "algorithmic bytes = N*s_Y + 4N (fp32 residual write) + 4M(I+J) + 8(I+J), this rank's shard"}
+    value = K / (ms * 1e-3)
+
+    # ---------------- e2e: the public API with host buffers ----------------------
+    e2e = None
+    if not args.no_e2e:
+        lib.scgbm_dev_free(ydev, device); ydev = None
+        nbytes = I * Jl * 4
+        pin = C.c_void_p()
+        t0 = time.perf_counter()
+        pinned = lib.scgbm_host_alloc_pinned(C.byref(pin), nbytes) == 0
+        if pinned:
+            Yh = np.frombuffer((C.c_int32 * (I * Jl)).from_address(pin.value), dtype=np.int32).reshape((I, Jl), order="F")
+        else:
+            log("pinned allocation failed, using pageable host memory")
+            Yh = np.empty((I, Jl), dtype=np.int32, order="F")
+        chunk = max(1, (512 << 20) // (I * 4))
+        dchunk = C.c_void_p()
+        L.check(lib.scgbm_dev_alloc(C.byref(dchunk), I * chunk * 4, device))
+        for c0 in range(0, Jl, chunk):
+            c1 = min(Jl, c0 + chunk)
+            wl.sim_into(lib, L, dchunk, j0 + c0, j0 + c1, I, L.I32, device)
+            L.check(lib.scgbm_memcpy_d2h(C.c_void_p(Yh.ctypes.data + c0 * I * 4), dchunk, I * (c1 - c0) * 4, device))
+        lib.scgbm_dev_free(dchunk, device)
+        log(f"rank {rank}: host int32 Y ({nbytes / 1e9:.1f} GB, pinned={pinned}) ready in {time.perf_counter() - t0:.1f}s")
+        barrier()
+        t0 = time.perf_counter()
+        out = gbm_sc(Yh, M, max_iter=args.e2e_max_iter, return_W=False, device=device, comm=comm, profile=True)
+        wall = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        prof = out["_prof"]
+        n_it = out["_n_iter"]
+        e2e = {"value": n_it / wall, "unit": "iters/s", "h2d_bytes_per_step": prof["h2d_bytes"] / n_it,
+               "d2h_bytes_per_step": prof["d2h_bytes"] / n_it, "fit_seconds": wall, "iterations": n_it,
+               "accepted": int(len(out["obj"])), "device_ms": prof["total_ms"], "host_dtype": "int32",
+               "pinned": bool(pinned), "objective_first_last": [float(out["obj"][0]), float(out["obj"][-1])],
+               "call": f"gbm_sc(Y, M={M}, max_iter={args.e2e_max_iter}, return_W=False) with reference defaults tol=1e-4, min_iter=30"}
+        del Yh
+        if pinned:
+            lib.scgbm_host_free_pinned(pin)
+    elif ydev is not None:
+        lib.scgbm_dev_free(ydev, device)
+
+    cb = None
+    if rank == 0 and not args.no_cpu and world == 1:
+        try:
+            cb = cpu_baseline(wl, M, 3, 1, args.cpu_sample_cells)
+        except Exception as e:  # pragma: no cover
+            log("cpu baseline failed:", e)
+
+    if comm is not None:
+        comm.destroy()
+    if dist is not None:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": "gbm_sc_iters_per_sec", "value": value, "unit": "iters/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 eta / f64 reductions and small dense", "data": "synthetic",
+        "config": {"workload": workload, "genes": I, "cells": J, "M": M, "y_device_format": "u16 (s_Y=2)",
+                   "sharding": f"cells over {world} rank(s)",
+                   "l2": "inputs (Y + fp32 residual) are far larger than the 126 MB L2; no flush needed",
+                   "svd": "block-Krylov, block M+12, adaptive depth, tol 1e-4", "svd_passes_per_step": svd_passes / K},
+        "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "clocks": clocks,
+        "gpu_launches": int(sum(launches.values())),
+        "kernel_ms_per_step": {k: v / K for k, v in kms.items()},
+        "launches_per_step": {k: v / K for k, v in launches.items()},
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -84,14 +84,11 @@ __global__ void ts_gram_reduce(int nchunk, int p, int q, const double* __restric
 void ts_gram(Ctx& ctx, SmallWs& ws, int64_t n, int p, int q, const double* A, int64_t lda,
              const double* B, int64_t ldb, double* C, int ldc, double alpha, double beta) {
   if (p <= 0 || q <= 0) return;
-  int64_t rows_per_chunk = 2048;
-  int nchunk = (int)ceil_div(n, rows_per_chunk);
-  const int max_chunks = ctx.num_sms * 4;
-  if (nchunk > max_chunks) {
-    rows_per_chunk = round_up(ceil_div(n, max_chunks), GR_KS);
-    nchunk = (int)ceil_div(n, rows_per_chunk);
-  }
-  if (nchunk < 1) nchunk = 1;
+  // enough chunks to fill the machine twice over, at least two smem slabs each
+  const int64_t blocks_pq = ceil_div(p, GR_TB) * ceil_div(q, GR_TB);
+  const int64_t want_chunks = std::max<int64_t>(1, ceil_div((int64_t)ctx.num_sms * 2, blocks_pq));
+  int64_t rows_per_chunk = std::max<int64_t>(2 * GR_KS, round_up(ceil_div(n, want_chunks), GR_KS));
+  int nchunk = (int)std::max<int64_t>(1, ceil_div(n, rows_per_chunk));
   ws.need_partial((int64_t)nchunk * p * q);
   ProfScope ps(ctx.prof, SCGBM_K_SMALL, 2);
   dim3 grid(nchunk, (unsigned)ceil_div(p, GR_TB), (unsigned)ceil_div(q, GR_TB));
@@ -192,144 +189,209 @@ __device__ __forceinline__ void jacobi_pair(int r, int k, int m, int& p, int& q)
   p = min(a, b); q = max(a, b);
 }
 
+__device__ __forceinline__ double block_sum_1024(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  const double out = red[0];
+  __syncthreads();
+  return out;
+}
+
+// A and V live in shared memory (leading dimension lds, odd so that row sweeps are
+// bank-conflict free) when they fit, else in global memory (L2-resident).
 __global__ void __launch_bounds__(JE_NT, 1)
 jacobi_eigh_kernel(int n, double* __restrict__ Ag, double* __restrict__ Vg, double* __restrict__ w,
-                   double* __restrict__ Vout, int use_smem, int max_sweeps, int* __restrict__ info) {
+                   double* __restrict__ Vout, int a_smem, int v_smem, int max_sweeps) {
   extern __shared__ double sm[];
   const int m = (n % 2 == 0) ? n : n + 1;   // virtual size (dummy index n when odd)
   const int half = m / 2;
+  const int lds = n | 1;
   double* cs = sm;                 // [half] cos
   double* sn = cs + half;          // [half] sin
-  double* red = sn + half;         // [32] reduction scratch
-  double* A = Ag;
-  double* V = Vg;
-  if (use_smem) {
-    A = red + 32;
-    V = A + (size_t)n * n;
-    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) A[idx] = Ag[idx];
+  double* red = sn + half;         // [32]
+  int* pq = reinterpret_cast<int*>(red + 32);   // [half] p | q << 16
+  double* nxt = reinterpret_cast<double*>(pq + ((half + 1) & ~1));
+  double* A = Ag; int lda = n;
+  double* V = Vg; int ldv = n;
+  if (a_smem) { A = nxt; lda = lds; nxt += (size_t)n * lds; }
+  if (v_smem) { V = nxt; ldv = lds; }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    const int i = idx % n, j = idx / n;
+    if (a_smem) A[(size_t)j * lda + i] = Ag[idx];
+    V[(size_t)j * ldv + i] = (i == j) ? 1.0 : 0.0;
   }
-  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) V[idx] = ((idx % n) == (idx / n)) ? 1.0 : 0.0;
   __syncthreads();
-
-  // Frobenius norm^2 for the stopping rule
   double loc = 0.0;
-  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) loc += A[idx] * A[idx];
-  loc = warp_sum(loc);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = loc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
-    v = warp_sum(v);
-    if (threadIdx.x == 0) red[0] = v;
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    const double a = A[(size_t)(idx / n) * lda + (idx % n)];
+    loc += a * a;
   }
-  __syncthreads();
-  const double fro2 = red[0];
-  __syncthreads();
+  const double fro2 = block_sum_1024(loc, red);
 
-  int sweeps_done = 0;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-    // off-diagonal norm^2
     double off = 0.0;
     for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
       const int i = idx % n, j = idx / n;
-      if (i != j) off += A[idx] * A[idx];
+      if (i != j) { const double a = A[(size_t)j * lda + i]; off += a * a; }
     }
-    off = warp_sum(off);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = off;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      double v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
-      v = warp_sum(v);
-      if (threadIdx.x == 0) red[0] = v;
-    }
-    __syncthreads();
-    const double off2 = red[0];
-    __syncthreads();
-    if (off2 <= 1e-30 * fro2 || fro2 == 0.0) break;
-    sweeps_done = sweep + 1;
+    const double off2 = block_sum_1024(off, red);
+    if (off2 <= 1e-28 * fro2 || fro2 == 0.0) break;
 
     for (int r = 0; r < m - 1; ++r) {
-      // 1. rotation angles
+      // 1. rotation angles for the half disjoint pairs of this round
       for (int k = threadIdx.x; k < half; k += blockDim.x) {
         int p, q;
         jacobi_pair(r, k, m, p, q);
         double c = 1.0, s = 0.0;
         if (q < n) {
-          const double apq = A[(size_t)q * n + p];
-          const double app = A[(size_t)p * n + p], aqq = A[(size_t)q * n + q];
-          if (fabs(apq) > 1e-300 && fabs(apq) > 1e-18 * sqrt(fabs(app * aqq)) ) {
+          const double apq = A[(size_t)q * lda + p];
+          const double app = A[(size_t)p * lda + p], aqq = A[(size_t)q * lda + q];
+          if (fabs(apq) > 1e-300 && fabs(apq) > 1e-17 * sqrt(fabs(app * aqq))) {
             const double tau = (aqq - app) / (2.0 * apq);
             const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-            c = 1.0 / sqrt(1.0 + t * t);
+            c = rsqrt(1.0 + t * t);
             s = t * c;
           }
+        } else {
+          q = -1;
         }
-        cs[k] = c; sn[k] = s;
+        cs[k] = c; sn[k] = s; pq[k] = (q < 0 || s == 0.0) ? -1 : (p | (q << 16));
       }
       __syncthreads();
-      // 2. columns: A <- A J,  V <- V J
-      for (int idx = threadIdx.x; idx < half * n; idx += blockDim.x) {
-        const int k = idx / n, i = idx % n;
-        int p, q;
-        jacobi_pair(r, k, m, p, q);
-        if (q >= n) continue;
+      // 2. columns: A <- A J, V <- V J   (one warp per pair, lanes over rows)
+      for (int k = warp; k < half; k += nwarps) {
+        const int code = pq[k];
+        if (code < 0) continue;
+        const int p = code & 0xffff, q = code >> 16;
         const double c = cs[k], s = sn[k];
-        if (s == 0.0) continue;
-        const double ap = A[(size_t)p * n + i], aq = A[(size_t)q * n + i];
-        A[(size_t)p * n + i] = c * ap - s * aq;
-        A[(size_t)q * n + i] = s * ap + c * aq;
-        const double vp = V[(size_t)p * n + i], vq = V[(size_t)q * n + i];
-        V[(size_t)p * n + i] = c * vp - s * vq;
-        V[(size_t)q * n + i] = s * vp + c * vq;
+        double* ap = A + (size_t)p * lda; double* aq = A + (size_t)q * lda;
+        double* vp = V + (size_t)p * ldv; double* vq = V + (size_t)q * ldv;
+        for (int i = lane; i < n; i += 32) {
+          const double x = ap[i], y = aq[i];
+          ap[i] = c * x - s * y; aq[i] = s * x + c * y;
+          const double u = vp[i], v = vq[i];
+          vp[i] = c * u - s * v; vq[i] = s * u + c * v;
+        }
       }
       __syncthreads();
-      // 3. rows: A <- J^T A
-      for (int idx = threadIdx.x; idx < half * n; idx += blockDim.x) {
-        const int k = idx % half, j = idx / half;
-        int p, q;
-        jacobi_pair(r, k, m, p, q);
-        if (q >= n) continue;
+      // 3. rows: A <- J^T A   (one warp per pair, lanes over columns)
+      for (int k = warp; k < half; k += nwarps) {
+        const int code = pq[k];
+        if (code < 0) continue;
+        const int p = code & 0xffff, q = code >> 16;
         const double c = cs[k], s = sn[k];
-        if (s == 0.0) continue;
-        const double ap = A[(size_t)j * n + p], aq = A[(size_t)j * n + q];
-        A[(size_t)j * n + p] = c * ap - s * aq;
-        A[(size_t)j * n + q] = s * ap + c * aq;
+        for (int j = lane; j < n; j += 32) {
+          double* col = A + (size_t)j * lda;
+          const double x = col[p], y = col[q];
+          col[p] = c * x - s * y; col[q] = s * x + c * y;
+        }
       }
       __syncthreads();
     }
   }
   // sort eigenvalues descending (rank by counting), write out
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double di = A[(size_t)i * n + i];
+  for (int i = warp; i < n; i += nwarps) {
+    const double di = A[(size_t)i * lda + i];
     int rank = 0;
-    for (int j = 0; j < n; ++j) {
-      const double dj = A[(size_t)j * n + j];
+    for (int j = lane; j < n; j += 32) {
+      const double dj = A[(size_t)j * lda + j];
       if (dj > di || (dj == di && j < i)) ++rank;
     }
-    w[rank] = di;
-    // stash the destination column in cs/sn space is too small for n; use red-free approach below
-    for (int k = 0; k < n; ++k) Vout[(size_t)rank * n + k] = V[(size_t)i * n + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+    if (lane == 0) w[rank] = di;
+    for (int k = lane; k < n; k += 32) Vout[(size_t)rank * n + k] = V[(size_t)i * ldv + k];
   }
-  if (threadIdx.x == 0 && info) info[0] = sweeps_done;
 }
 
 void eigh_desc(Ctx& ctx, SmallWs& ws, int n, double* A, double* w, double* Vout) {
   SCGBM_REQUIRE(n >= 1 && n <= 1024, "eigh_desc: n out of range");
   const int m = (n % 2 == 0) ? n : n + 1;
-  size_t base = (size_t)(m + 32) * sizeof(double);
-  size_t full = base + (size_t)2 * n * n * sizeof(double);
-  int use_smem = full <= 200 * 1024;
-  size_t smem = use_smem ? full : base;
+  const int lds = n | 1;
+  const size_t base = (size_t)(m + 32) * sizeof(double) + (size_t)((m / 2 + 1) & ~1) * sizeof(int) + 16;
+  const size_t mat = (size_t)n * lds * sizeof(double);
+  const size_t cap = 220 * 1024;
+  const int a_smem = base + mat <= cap;
+  const int v_smem = a_smem && base + 2 * mat <= cap;
+  const size_t smem = base + (a_smem ? mat : 0) + (v_smem ? mat : 0);
   ws.need_eigV((int64_t)n * n);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SCGBM_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024));
-    attr_set = true;
-  }
+  SCGBM_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
   ProfScope ps(ctx.prof, SCGBM_K_SMALL, 1);
-  int threads = n <= 32 ? 256 : (n <= 64 ? 512 : JE_NT);
-  jacobi_eigh_kernel<<<1, threads, smem, ctx.stream>>>(n, A, ws.eigV.get(), w, Vout, use_smem, 40, nullptr);
+  int threads = n <= 16 ? 256 : (n <= 32 ? 512 : JE_NT);
+  jacobi_eigh_kernel<<<1, threads, smem, ctx.stream>>>(n, A, ws.eigV.get(), w, Vout, a_smem, v_smem, 40);
   SCGBM_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------
+// chol_inv: S (b x b SPD Gram, col-major) -> E = L^{-T} so that K E is orthonormal when
+// S = K^T K (CholeskyQR).  Sets *flag when a pivot is too small (rank-deficient block).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+chol_inv_kernel(int b, const double* __restrict__ S, double* __restrict__ E, int* __restrict__ flag) {
+  extern __shared__ double smc[];
+  const int ld = b | 1;
+  double* Lm = smc;                    // [b][ld] row-major lower triangle
+  double* X = Lm + (size_t)b * ld;     // [b][ld] inverse of L (lower)
+  __shared__ int bad;
+  __shared__ double dmax;
+  if (threadIdx.x == 0) { bad = 0; dmax = 0.0; }
+  for (int idx = threadIdx.x; idx < b * b; idx += blockDim.x) {
+    const int i = idx % b, j = idx / b;
+    Lm[(size_t)i * ld + j] = S[idx];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double d = 0.0;
+    for (int i = 0; i < b; ++i) d = fmax(d, Lm[(size_t)i * ld + i]);
+    dmax = d;
+  }
+  __syncthreads();
+  for (int k = 0; k < b; ++k) {
+    const double akk = Lm[(size_t)k * ld + k];
+    if (!(akk > 1e-10 * dmax) || !(akk > 0.0)) { if (threadIdx.x == 0) bad = 1; __syncthreads(); break; }
+    const double lkk = sqrt(akk);
+    __syncthreads();
+    for (int i = k + threadIdx.x; i < b; i += blockDim.x)
+      Lm[(size_t)i * ld + k] = (i == k) ? lkk : Lm[(size_t)i * ld + k] / lkk;
+    __syncthreads();
+    // trailing update, lower triangle only
+    const int rem = b - k - 1;
+    for (int idx = threadIdx.x; idx < rem * rem; idx += blockDim.x) {
+      const int i = k + 1 + idx / rem, j = k + 1 + idx % rem;
+      if (j <= i) Lm[(size_t)i * ld + j] -= Lm[(size_t)i * ld + k] * Lm[(size_t)j * ld + k];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (bad) {
+    if (threadIdx.x == 0) atomicExch(flag, 1);
+    for (int idx = threadIdx.x; idx < b * b; idx += blockDim.x) E[idx] = (idx % b == idx / b) ? 1.0 : 0.0;
+    return;
+  }
+  // X = L^{-1}: thread c solves column c by forward substitution
+  for (int c = threadIdx.x; c < b; c += blockDim.x) {
+    for (int i = 0; i < b; ++i) {
+      if (i < c) { X[(size_t)i * ld + c] = 0.0; continue; }
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int k = c; k < i; ++k) s -= Lm[(size_t)i * ld + k] * X[(size_t)k * ld + c];
+      X[(size_t)i * ld + c] = s / Lm[(size_t)i * ld + i];
+    }
+  }
+  __syncthreads();
+  // E = X^T (upper triangular), column-major: E[i + j b] = X[j][i]
+  for (int idx = threadIdx.x; idx < b * b; idx += blockDim.x) {
+    const int i = idx % b, j = idx / b;
+    E[idx] = X[(size_t)j * ld + i];
+  }
 }
 
 // ---------------------------------------------------------------------------------
@@ -361,11 +423,12 @@ void copy_mat(Ctx& ctx, int64_t n, int q, const double* src, int64_t lds, double
   SCGBM_LAUNCH_CHECK();
 }
 
-// K (n x b, ldk) <- orthonormal basis of span(K) orthogonal to Qb (n x pb); columns
-// whose direction is numerically absent become zero.  Two rounds (CholeskyQR2-like,
-// but through the eigendecomposition of the Gram so rank deficiency is harmless).
+// K (n x b, ldk) <- orthonormal basis of span(K) orthogonal to Qb (n x pb).  Fast path:
+// CholeskyQR2 (Gram -> Cholesky -> K L^{-T}); a too-small pivot raises *chol_flag and
+// the caller redoes the whole SVD call with robust = true, where the Gram is
+// eigendecomposed instead and numerically absent directions become zero columns.
 void sym_orth(Ctx& ctx, SmallWs& ws, int64_t n, int b, double* K, int64_t ldk, const double* Qb,
-              int64_t ldq, int pb, double* tmp_nb /* n x b scratch, ld = ldk */) {
+              int64_t ldq, int pb, double* tmp_nb /* n x b scratch, ld = ldk */, bool robust, int* chol_flag) {
   ws.need_small((int64_t)std::max(pb, b) * b + 3 * (int64_t)b * b + b);
   double* C = ws.small.get();                       // pb x b
   double* S = C + (int64_t)std::max(pb, b) * b;     // b x b
@@ -377,10 +440,18 @@ void sym_orth(Ctx& ctx, SmallWs& ws, int64_t n, int b, double* K, int64_t ldk, c
       ts_mul(ctx, n, pb, b, Qb, ldq, C, pb, K, ldk, -1.0, 1.0);
     }
     ts_gram(ctx, ws, n, b, b, K, ldk, K, ldk, S, b, 1.0, 0.0);
-    eigh_desc(ctx, ws, b, S, lam, E);
-    {
+    if (robust) {
+      eigh_desc(ctx, ws, b, S, lam, E);
       ProfScope ps(ctx.prof, SCGBM_K_SMALL, 1);
       scale_cols_invsqrt<<<(unsigned)ceil_div(b * b, 256), 256, 0, ctx.stream>>>(b, E, lam, 1e-12);
+      SCGBM_LAUNCH_CHECK();
+    } else {
+      const size_t smem = 2 * (size_t)b * (b | 1) * sizeof(double);
+      SCGBM_REQUIRE(smem <= 200 * 1024, "sym_orth: block too large for the shared-memory Cholesky");
+      if (smem > 48 * 1024)
+        SCGBM_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ProfScope ps(ctx.prof, SCGBM_K_SMALL, 1);
+      chol_inv_kernel<<<1, 256, smem, ctx.stream>>>(b, S, E, chol_flag);
       SCGBM_LAUNCH_CHECK();
     }
     ts_mul(ctx, n, b, b, K, ldk, E, b, tmp_nb, ldk, 1.0, 0.0);

@@ -30,6 +30,6 @@ void copy_mat(Ctx& ctx, int64_t n, int q, const double* src, int64_t lds, double
 
 // K <- orthonormal basis of span(K) minus span(Qb); rank-deficient directions -> 0
 void sym_orth(Ctx& ctx, SmallWs& ws, int64_t n, int b, double* K, int64_t ldk, const double* Qb,
-              int64_t ldq, int pb, double* tmp_nb);
+              int64_t ldq, int pb, double* tmp_nb, bool robust, int* chol_flag);
 
 }  // namespace scgbm

@@ -391,6 +391,8 @@ struct FitRun {
     const int M = st.M, nbatch = st.nbatch;
     const Factor& fc = st.slot[cur];
     const XDesc xc = st.desc(fc);
+    static const bool trace = getenv("SCGBM_TRACE") != nullptr;
+    const double tr0 = trace ? now_sec() : 0.0;
     // (a) alphas <- log.rsy - log(rowSums(exp(X + betas)))      R/fit.R:127-130
     st.stage_cols();
     pass_rowsum(ctx, st.eta, st.geom, xc, st.g_col.get(), st.S.get());
@@ -422,6 +424,7 @@ struct FitRun {
     double h[3];
     SCGBM_CUDA(cudaMemcpyAsync(h, st.scal.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
     ctx.sync();
+    const double tr1 = trace ? now_sec() : 0.0;
     {                                                    // R/fit.R:139-142
       const double t = now_sec();
       t_cum += t - t_prev; t_prev = t;
@@ -436,7 +439,8 @@ struct FitRun {
     if (std::isnan(ll) || std::isinf(ll)) {              // R/fit.R:152-157
       revert();
       lr = lr / 2;
-      return true;
+      if (i >= a.max_iter) finished = true;
+      return !finished;
     }
     if (i >= 3) {                                        // R/fit.R:158
       const double tau = std::fabs((ll - LL[i - 3]) / ll);
@@ -447,7 +451,8 @@ struct FitRun {
       if (ll < llp) {                                    // R/fit.R:164-167
         lr = std::max(lr / 2, 1.0);
         revert();
-        return true;
+        if (i >= a.max_iter) finished = true;
+        return !finished;
       } else {
         lr = lr * 1.05;                                  // R/fit.R:169
       }
@@ -480,8 +485,16 @@ struct FitRun {
     Factor& fn = st.slot[next];
     fn.kind = XK_LOWRANK; fn.M = M;
     TsvdOpts o = st.opts();
-    tsvd(ctx, st.svd, op, o, fn.U.get(), fn.d.get(), fn.V.get(), nullptr, nullptr);   // R/fit.R:323
+    int svd_passes = 0;
+    double svd_est = 0.0;
+    tsvd(ctx, st.svd, op, o, fn.U.get(), fn.d.get(), fn.V.get(), &svd_passes, &svd_est);   // R/fit.R:323
     st.stage_factor(fn);                                 // X <- u d v^T (never materialised; R/fit.R:324)
+    if (trace) {
+      ctx.sync();
+      const double tr2 = now_sec();
+      fprintf(stderr, "[scgbm-trace] iter %d: eta passes %.2f ms, svd %.2f ms (%d passes, est %.2e)\n", i,
+              (tr1 - tr0) * 1e3, (tr2 - tr1) * 1e3, svd_passes, svd_est);
+    }
     prev = cur; cur = next; last = next;                 // R/fit.R:179-180,320
     if (i == a.max_iter) { hit_max = 1; finished = true; return false; }   // R/fit.R:182-185
     return true;
@@ -720,19 +733,7 @@ void dbg_tsvd_impl(const scgbm_tsvd_args* a, scgbm_tsvd_out* out) {
   o.seed = a->seed;
   o.variant = a->kernel_variant;
   TsvdWs ws;
-  if (a->V0) {
-    const int b = (int)std::min<int64_t>(M + o.extra, std::min(I, J));
-    ws.b = b;
-    int depth = (int)std::min<int64_t>(o.depth, std::max<int64_t>(0, std::min(I, J) / b - 1));
-    const int pmax = b * (depth + 1);
-    ws.Qb.alloc(ldI * pmax); ws.Zb.alloc(ldJ * pmax); ws.Kb.alloc(ldI * b);
-    ws.tmpI.alloc(ldI * b); ws.tmpJ.alloc(ldJ * b);
-    ws.T.alloc((int64_t)pmax * pmax); ws.Tw.alloc((int64_t)pmax * pmax); ws.S.alloc((int64_t)pmax * pmax);
-    ws.theta.alloc(pmax); ws.est.alloc(2);
-    ws.Ub.alloc(ldI * b); ws.Vb.alloc(ldJ * b); ws.Vwarm.alloc(ldJ * b);
-    upload_padded(ctx, a->V0, J, b, ldJ, ws.Vwarm.get());
-    ws.warm = true;
-  }
+  if (a->V0) tsvd_set_warm_start(ctx, ws, op, o, a->V0);
   DevBuf<double> U(ldI * M), D(M), V(ldJ * M);
   int passes = 0;
   double est = 0;

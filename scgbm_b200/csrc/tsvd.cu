@@ -61,7 +61,7 @@ __global__ void copy_lead_kernel(int p, const double* __restrict__ T, int ldT, d
 // est = max_{k<M} sqrt(s_kt^T T_tt s_kt) * sqrt(theta_0) / theta_k
 __global__ void ritz_est_kernel(int p, int b, int tb, int M, const double* __restrict__ S,
                                 const double* __restrict__ theta, const double* __restrict__ T, int ldT,
-                                double* __restrict__ est) {
+                                double* __restrict__ est, const int* __restrict__ flag) {
   __shared__ double red[64];
   double e = 0.0;
   for (int k = threadIdx.x; k < M; k += blockDim.x) {
@@ -84,6 +84,7 @@ __global__ void ritz_est_kernel(int p, int b, int tb, int M, const double* __res
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
     est[0] = m;
     est[1] = theta[0];
+    est[2] = (double)flag[0];
   }
 }
 
@@ -139,95 +140,134 @@ static void op_tmul(Ctx& ctx, TsvdWs& ws, const GOperator& op, const double* Q, 
   if (op.R && op.c != 0.0) prod_t(ctx, ws.prod, op.R, op.I, op.ldI, op.J, Q, ldQ, b, op.c, out, op.ldJ, variant);
 }
 
+static void tsvd_alloc(TsvdWs& ws, int64_t ldI, int64_t ldJ, int b, int pmax, int maxM) {
+  if (ws.b != b || ws.pmax < pmax || ws.Zb.n < ldJ * pmax || ws.Qb.n < ldI * pmax) {
+    ws.b = b;
+    ws.pmax = pmax;
+    ws.warm = false;
+    ws.Qb.alloc(ldI * pmax); ws.Zb.alloc(ldJ * pmax);
+    ws.tmpI.alloc(ldI * b);
+    ws.T.alloc((int64_t)pmax * pmax); ws.Tw.alloc((int64_t)pmax * pmax); ws.S.alloc((int64_t)pmax * pmax);
+    ws.theta.alloc(pmax); ws.est.alloc(4); ws.flag.alloc(1);
+    ws.Ub.alloc(ldI * b); ws.Vb.alloc(ldJ * b); ws.Vwarm.alloc(ldJ * b);
+  }
+  if (ws.C.n < (int64_t)std::max(maxM, pmax) * b) ws.C.alloc((int64_t)std::max(maxM, pmax) * b);
+}
+
+void tsvd_set_warm_start(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, const double* V0_host) {
+  const int64_t minIJ = std::min(op.I, op.J_total);
+  const int b = (int)std::min<int64_t>(o.M + std::max(o.extra, 0), minIJ);
+  int depth = (int)std::min<int64_t>(std::max(0, o.depth), std::max<int64_t>(0, minIJ / b - 1));
+  int maxM = 1;
+  for (int t = 0; t < op.nterms; ++t) maxM = std::max(maxM, op.t[t].M);
+  tsvd_alloc(ws, op.ldI, op.ldJ, b, b * (depth + 1), maxM);
+  SCGBM_CUDA(cudaMemsetAsync(ws.Vwarm.get(), 0, (size_t)op.ldJ * b * sizeof(double), ctx.stream));
+  SCGBM_CUDA(cudaMemcpy2DAsync(ws.Vwarm.get(), op.ldJ * sizeof(double), V0_host, op.J * sizeof(double),
+                               op.J * sizeof(double), b, cudaMemcpyHostToDevice, ctx.stream));
+  ws.warm = true;
+}
+
 void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* outU, double* outD,
           double* outV, int* passes_out, double* est_out) {
   const int M = o.M;
   const int64_t minIJ = std::min(op.I, op.J_total);
   SCGBM_REQUIRE(M >= 1 && M <= minIJ, "M must be between 1 and min(I, J)");
-  int b = (int)std::min<int64_t>(M + std::max(o.extra, 0), minIJ);
-  int depth = std::max(0, o.depth);
+  const int b = (int)std::min<int64_t>(M + std::max(o.extra, 0), minIJ);
   // keep the Krylov basis inside the space: b * (depth + 1) <= min(I, J)
-  depth = (int)std::min<int64_t>(depth, std::max<int64_t>(0, minIJ / b - 1));
-  const int pmax = b * (depth + 1);
+  const int depth_cap = (int)std::max<int64_t>(0, minIJ / b - 1);
+  const int depth_warm = std::min(std::max(0, o.depth), depth_cap);
+  const int depth_cold = std::min(std::max(depth_warm, o.cold_depth), depth_cap);
   const int64_t ldI = op.ldI, ldJ = op.ldJ;
   int maxM = 1;
   for (int t = 0; t < op.nterms; ++t) maxM = std::max(maxM, op.t[t].M);
-
-  if (ws.b != b || ws.Zb.n < ldJ * pmax || ws.Qb.n < ldI * pmax) {
-    ws.b = b;
-    ws.warm = false;
-    ws.Qb.alloc(ldI * pmax); ws.Zb.alloc(ldJ * pmax); ws.Kb.alloc(ldI * b);
-    ws.tmpI.alloc(ldI * b); ws.tmpJ.alloc(ldJ * b);
-    ws.T.alloc((int64_t)pmax * pmax); ws.Tw.alloc((int64_t)pmax * pmax); ws.S.alloc((int64_t)pmax * pmax);
-    ws.theta.alloc(pmax); ws.est.alloc(2);
-    ws.Ub.alloc(ldI * b); ws.Vb.alloc(ldJ * b); ws.Vwarm.alloc(ldJ * b);
-  }
-  if (ws.C.n < (int64_t)std::max(maxM, pmax) * b) ws.C.alloc((int64_t)std::max(maxM, pmax) * b);
-  // pad rows of the gene-side buffers must be zero for prod_t's operand conversion
-  ws.Qb.zero(ctx.stream); ws.Kb.zero(ctx.stream);
+  const bool was_warm = ws.warm && ws.b == b;
+  tsvd_alloc(ws, ldI, ldJ, b, b * ((was_warm ? depth_warm : depth_cold) + 1), maxM);
+  const int pmax = ws.pmax;
+  const int depth = std::min(was_warm ? depth_warm : depth_cold, pmax / b - 1);
 
   int passes = 0;
   double est = 1e300;
-  const double* V0 = nullptr;
-  if (ws.warm) {
-    V0 = ws.Vwarm.get();
-  } else {
-    ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
-    fill_normal_kernel<<<(unsigned)ceil_div(op.J * b, 256), 256, 0, ctx.stream>>>(
-        op.J, b, ldJ, o.seed, (uint64_t)ctx.rank << 40, ws.Vb.get());
-    SCGBM_LAUNCH_CHECK();
-    V0 = ws.Vb.get();
-  }
-  const bool was_warm = ws.warm;
-  int p = b;
-  for (int cycle = 0;; ++cycle) {
-    ws.T.zero(ctx.stream);
-    op_mul(ctx, ws, op, V0, ldJ, b, ws.Qb.get(), o.variant);
-    ++passes;
-    sym_orth(ctx, ws.small, ldI, b, ws.Qb.get(), ldI, nullptr, ldI, 0, ws.tmpI.get());
-    int t = 0;
-    for (;; ++t) {
-      p = b * (t + 1);
-      double* Zt = ws.Zb.get() + (int64_t)t * b * ldJ;
-      op_tmul(ctx, ws, op, ws.Qb.get() + (int64_t)t * b * ldI, ldI, b, Zt, o.variant);
+  bool robust = ws.robust;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    bool restart = false;
+    ws.flag.zero(ctx.stream);
+    const double* V0 = nullptr;
+    if (was_warm) {
+      V0 = ws.Vwarm.get();
+    } else {
+      ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
+      fill_normal_kernel<<<(unsigned)ceil_div(op.J * b, 256), 256, 0, ctx.stream>>>(
+          op.J, b, ldJ, o.seed, (uint64_t)ctx.rank << 40, ws.Vb.get());
+      SCGBM_LAUNCH_CHECK();
+      V0 = ws.Vb.get();
+    }
+    int p = b;
+    for (int cycle = 0; !restart; ++cycle) {
+      ws.T.zero(ctx.stream);
+      op_mul(ctx, ws, op, V0, ldJ, b, ws.Qb.get(), o.variant);
       ++passes;
-      // Gram block column  Zb[:, :p]^T Z_t  (p x b), all ranks
-      ts_gram(ctx, ws.small, op.J, p, b, ws.Zb.get(), ldJ, Zt, ldJ, ws.C.get(), p, 1.0, 0.0);
-      ctx.allreduce_sum(ws.C.get(), (int64_t)p * b);
-      {
-        ProfScope ps(ctx.prof, SCGBM_K_SMALL, 2);
-        scatter_T_kernel<<<(unsigned)ceil_div(p * b, 256), 256, 0, ctx.stream>>>(p, b, t * b, ws.C.get(), ws.T.get(), pmax);
-        copy_lead_kernel<<<(unsigned)ceil_div(p * p, 256), 256, 0, ctx.stream>>>(p, ws.T.get(), pmax, ws.Tw.get());
-        SCGBM_LAUNCH_CHECK();
+      sym_orth(ctx, ws.small, ldI, b, ws.Qb.get(), ldI, nullptr, ldI, 0, ws.tmpI.get(), robust, ws.flag.get());
+      for (int t = 0;; ++t) {
+        p = b * (t + 1);
+        double* Zt = ws.Zb.get() + (int64_t)t * b * ldJ;
+        op_tmul(ctx, ws, op, ws.Qb.get() + (int64_t)t * b * ldI, ldI, b, Zt, o.variant);
+        ++passes;
+        // Gram block column  Zb[:, :p]^T Z_t  (p x b), all ranks
+        ts_gram(ctx, ws.small, op.J, p, b, ws.Zb.get(), ldJ, Zt, ldJ, ws.C.get(), p, 1.0, 0.0);
+        ctx.allreduce_sum(ws.C.get(), (int64_t)p * b);
+        {
+          ProfScope ps(ctx.prof, SCGBM_K_SMALL, 1);
+          scatter_T_kernel<<<(unsigned)ceil_div(p * b, 256), 256, 0, ctx.stream>>>(p, b, t * b, ws.C.get(), ws.T.get(), pmax);
+          SCGBM_LAUNCH_CHECK();
+        }
+        // Ritz pairs are only needed where a stopping decision can be taken: never after
+        // the first block (the estimate cannot be small there), every block when warm,
+        // every other block on a cold start, and always at the end of the cycle
+        const bool last = t >= depth;
+        const bool check = last || (t >= 1 && (was_warm || (t % 2 == 1)));
+        if (check) {
+          {
+            ProfScope ps(ctx.prof, SCGBM_K_SMALL, 1);
+            copy_lead_kernel<<<(unsigned)ceil_div(p * p, 256), 256, 0, ctx.stream>>>(p, ws.T.get(), pmax, ws.Tw.get());
+            SCGBM_LAUNCH_CHECK();
+          }
+          eigh_desc(ctx, ws.small, p, ws.Tw.get(), ws.theta.get(), ws.S.get());
+          {
+            ProfScope ps(ctx.prof, SCGBM_K_SMALL, 1);
+            ritz_est_kernel<<<1, 64, 0, ctx.stream>>>(p, b, t * b, M, ws.S.get(), ws.theta.get(), ws.T.get(), pmax,
+                                                      ws.est.get(), ws.flag.get());
+            SCGBM_LAUNCH_CHECK();
+          }
+          double h[3];
+          SCGBM_CUDA(cudaMemcpyAsync(h, ws.est.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
+          ctx.sync();
+          est = h[0];
+          if (!(h[1] == h[1])) throw Error(SCGBM_ERR_NUMERIC, "truncated SVD: non-finite Ritz values");
+          if (h[2] != 0.0 && !robust) { restart = true; break; }   // a Cholesky pivot vanished: redo robustly
+          if (t > 0 && est < o.tol) break;
+        }
+        if (last) break;
+        op_mul(ctx, ws, op, Zt, ldJ, b, ws.Qb.get() + (int64_t)(t + 1) * b * ldI, o.variant);
+        ++passes;
+        sym_orth(ctx, ws.small, ldI, b, ws.Qb.get() + (int64_t)(t + 1) * b * ldI, ldI, ws.Qb.get(), ldI, p,
+                 ws.tmpI.get(), robust, ws.flag.get());
       }
-      eigh_desc(ctx, ws.small, p, ws.Tw.get(), ws.theta.get(), ws.S.get());
+      if (restart) break;
+      // Ritz vectors of the leading b pairs
       {
         ProfScope ps(ctx.prof, SCGBM_K_SMALL, 1);
-        ritz_est_kernel<<<1, 64, 0, ctx.stream>>>(p, b, t * b, M, ws.S.get(), ws.theta.get(), ws.T.get(), pmax, ws.est.get());
+        ritz_scale_kernel<<<(unsigned)ceil_div(p * b, 256), 256, 0, ctx.stream>>>(p, b, ws.S.get(), ws.theta.get(), ws.C.get(), ws.Tw.get());
         SCGBM_LAUNCH_CHECK();
       }
-      double h[2];
-      SCGBM_CUDA(cudaMemcpyAsync(h, ws.est.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
-      ctx.sync();
-      est = h[0];
-      if (!(h[1] == h[1])) throw Error(SCGBM_ERR_NUMERIC, "truncated SVD: non-finite Ritz values");
-      if (t > 0 && est < o.tol) break;
-      if (t >= depth) break;
-      op_mul(ctx, ws, op, Zt, ldJ, b, ws.Qb.get() + (int64_t)(t + 1) * b * ldI, o.variant);
-      ++passes;
-      sym_orth(ctx, ws.small, ldI, b, ws.Qb.get() + (int64_t)(t + 1) * b * ldI, ldI, ws.Qb.get(), ldI, p, ws.tmpI.get());
+      ts_mul(ctx, ldI, p, b, ws.Qb.get(), ldI, ws.S.get(), p, ws.Ub.get(), ldI, 1.0, 0.0);
+      ts_mul(ctx, op.J, p, b, ws.Zb.get(), ldJ, ws.C.get(), p, ws.Vwarm.get(), ldJ, 1.0, 0.0);
+      const bool converged = est < o.tol || depth == 0;
+      if (converged || cycle + 1 >= o.max_cycles || (was_warm && cycle >= 1)) break;
+      V0 = ws.Vwarm.get();
     }
-    // Ritz vectors of the leading b pairs
-    {
-      ProfScope ps(ctx.prof, SCGBM_K_SMALL, 1);
-      ritz_scale_kernel<<<(unsigned)ceil_div(p * b, 256), 256, 0, ctx.stream>>>(p, b, ws.S.get(), ws.theta.get(), ws.C.get(), ws.Tw.get());
-      SCGBM_LAUNCH_CHECK();
-    }
-    ts_mul(ctx, ldI, p, b, ws.Qb.get(), ldI, ws.S.get(), p, ws.Ub.get(), ldI, 1.0, 0.0);
-    ts_mul(ctx, op.J, p, b, ws.Zb.get(), ldJ, ws.C.get(), p, ws.Vwarm.get(), ldJ, 1.0, 0.0);
-    const bool converged = est < o.tol || depth == 0;
-    if (converged || cycle + 1 >= o.max_cycles || (was_warm && cycle >= 1)) break;
-    V0 = ws.Vwarm.get();
+    if (!restart) break;
+    robust = true;
+    ws.robust = true;   // the operator family of this fit is rank deficient: stay robust
   }
   ws.warm = true;
   copy_mat(ctx, ldI, M, ws.Ub.get(), ldI, outU, ldI);

@@ -30,7 +30,8 @@ struct GOperator {
 struct TsvdOpts {
   int M = 0;
   int extra = 12;       // block = M + extra
-  int depth = 3;        // Krylov extensions per cycle
+  int depth = 3;        // Krylov extensions per cycle (warm start)
+  int cold_depth = 7;   // ... on a cold start (fewer restarts)
   double tol = 1e-4;    // Ritz residual estimate
   int max_cycles = 40;  // restarts (cold start on gap-less spectra)
   uint64_t seed = 0;
@@ -40,7 +41,10 @@ struct TsvdOpts {
 struct TsvdWs {
   SmallWs small;
   ProdWs prod;
-  DevBuf<double> Qb, Zb, Kb, tmpI, tmpJ, T, Tw, S, theta, C, est, Ub, Vb;
+  DevBuf<double> Qb, Zb, tmpI, T, Tw, S, theta, C, est, Ub, Vb;
+  DevBuf<int> flag;       // set by the Cholesky orthonormalisation when a pivot vanishes
+  bool robust = false;    // eigen-based orthonormalisation (rank-deficient operators)
+  int pmax = 0;
   DevBuf<double> Vwarm;   // ldJ x b warm start for the next call
   bool warm = false;
   int b = 0;
@@ -48,6 +52,9 @@ struct TsvdWs {
 };
 
 // outU: ldI x M, outD: M, outV: ldJ x M (device, column-major)
+// upload a J x b start block (host, column-major) as the warm start of the next call
+void tsvd_set_warm_start(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, const double* V0_host);
+
 void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* outU, double* outD,
           double* outV, int* passes_out, double* est_out);
 
