@@ -281,6 +281,32 @@ typedef struct scgbm_tsvd_out {
 
 int scgbm_dbg_tsvd(const scgbm_tsvd_args* args, scgbm_tsvd_out* out);
 
+/* the two tall-skinny residual products of K5 on a given residual:
+ *   outN (I x b) = c * R P,   outT (J x b) = c * R^T Q
+ * R: I x J fp32 host (stored on device as bf16 hi/lo planes like the fit does);
+ * variant: 1 = CUDA-core kernels, 2 = tcgen05 kernels.  ms_n / ms_t: CUDA-event time of
+ * `reps` back-to-back launches of each product (mean per launch). */
+typedef struct scgbm_prod_args {
+  int64_t I, J;
+  const float* R;
+  const double* P;   /* J x b */
+  const double* Q;   /* I x b */
+  int32_t b;
+  double  c;
+  int32_t variant;
+  int32_t reps;
+  int32_t device;
+} scgbm_prod_args;
+
+typedef struct scgbm_prod_out {
+  double* outN;      /* I x b */
+  double* outT;      /* J x b */
+  double* Rq;        /* I x J or NULL: hi + lo as stored (the matrix the products really use) */
+  double  ms_n, ms_t;
+} scgbm_prod_out;
+
+int scgbm_dbg_prod(const scgbm_prod_args* args, scgbm_prod_out* out);
+
 /* one evaluation of the loop body up to the objective (R/fit.R:127-151) for given
  * X = Xu Xv^T (optionally clamped to +-8), beta in / alpha,beta out. */
 typedef struct scgbm_eval_args {

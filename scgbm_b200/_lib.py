@@ -110,6 +110,17 @@ class TsvdOut(C.Structure):
                 ("est", C.c_double)]
 
 
+class ProdArgs(C.Structure):
+    _fields_ = [("I", C.c_int64), ("J", C.c_int64), ("R", C.c_void_p), ("P", C.c_void_p), ("Q", C.c_void_p),
+                ("b", C.c_int32), ("c", C.c_double), ("variant", C.c_int32), ("reps", C.c_int32),
+                ("device", C.c_int32)]
+
+
+class ProdOut(C.Structure):
+    _fields_ = [("outN", C.c_void_p), ("outT", C.c_void_p), ("Rq", C.c_void_p), ("ms_n", C.c_double),
+                ("ms_t", C.c_double)]
+
+
 class EvalArgs(C.Structure):
     _fields_ = [("Y", C.c_void_p), ("y_dtype", C.c_int32), ("I", C.c_int64), ("J", C.c_int64),
                 ("ldY", C.c_int64), ("y_storage", C.c_int32),
@@ -131,7 +142,7 @@ EXPORTS = [
     "scgbm_host_alloc_pinned", "scgbm_host_free_pinned", "scgbm_flush_l2",
     "scgbm_comm_unique_id", "scgbm_comm_init_rank", "scgbm_comm_destroy", "scgbm_comm_allreduce_f64",
     "scgbm_last_error", "scgbm_device_count", "scgbm_version",
-    "scgbm_dbg_tsvd", "scgbm_dbg_eval", "scgbm_dbg_eigh",
+    "scgbm_dbg_tsvd", "scgbm_dbg_eval", "scgbm_dbg_eigh", "scgbm_dbg_prod",
 ]
 
 _lib = None
@@ -169,6 +180,7 @@ def load():
     lib.scgbm_comm_destroy.argtypes = [C.c_void_p]
     lib.scgbm_comm_allreduce_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
     lib.scgbm_dbg_tsvd.argtypes = [C.POINTER(TsvdArgs), C.POINTER(TsvdOut)]
+    lib.scgbm_dbg_prod.argtypes = [C.POINTER(ProdArgs), C.POINTER(ProdOut)]
     lib.scgbm_dbg_eval.argtypes = [C.POINTER(EvalArgs), C.POINTER(EvalOut)]
     lib.scgbm_dbg_eigh.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
     _lib = lib

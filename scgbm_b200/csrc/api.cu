@@ -21,6 +21,7 @@ void project_impl(const scgbm_proj_args* a, scgbm_proj_out* out);
 void sim_counts(const scgbm_sim_args* a, void* Y_dev, int64_t* n_saturated);
 void dbg_tsvd_impl(const scgbm_tsvd_args* a, scgbm_tsvd_out* out);
 void dbg_eval_impl(const scgbm_eval_args* a, scgbm_eval_out* out);
+void dbg_prod_impl(const scgbm_prod_args* a, scgbm_prod_out* out);
 }  // namespace scgbm
 
 using namespace scgbm;
@@ -147,6 +148,7 @@ int scgbm_device_count(void) {
 int scgbm_version(void) { return SCGBM_VERSION; }
 
 int scgbm_dbg_tsvd(const scgbm_tsvd_args* args, scgbm_tsvd_out* out) { return guarded([&] { dbg_tsvd_impl(args, out); }); }
+int scgbm_dbg_prod(const scgbm_prod_args* args, scgbm_prod_out* out) { return guarded([&] { dbg_prod_impl(args, out); }); }
 int scgbm_dbg_eval(const scgbm_eval_args* args, scgbm_eval_out* out) { return guarded([&] { dbg_eval_impl(args, out); }); }
 int scgbm_dbg_eigh(double* A, double* w, int32_t n, int32_t device) {
   return guarded([&] {

@@ -8,6 +8,7 @@
 //   fused  : W = min(exp(alpha+beta+X), max.Y); sum W; sum_nz Y log W;
 //            max W; resid = Y - W                                       R/fit.R:136-151,321,323
 #include "eta_pass.cuh"
+#include "products.cuh"
 
 namespace scgbm {
 
@@ -23,8 +24,8 @@ struct EtaParams {
   const int32_t* batch;
   const float* A; const float* B; int M; int clamp; const float* rowscale;
   const float* f_row; const float* g_col; const float* la_row; const float* lb_col;
-  const void* Y; float* R;
-  float maxY, log_maxY, coef;
+  const void* Y; uint16_t* Rhi; uint16_t* Rlo;
+  float maxY, log_maxY, coef, rscale;
   int tiles_per_chunk; int nJt;
   double* row_part; double* scal_part;
 };
@@ -162,12 +163,14 @@ eta_rows_kernel(const EtaParams p) {
           if (p.clamp) x = clamp8(x);
           xv[a] = x;
         }
-        float* rp = p.R + j * p.ldI + ig;
+        ushort4* rph = reinterpret_cast<ushort4*>(p.Rhi + j * p.ldI + ig);
+        ushort4* rpl = reinterpret_cast<ushort4*>(p.Rlo + j * p.ldI + ig);
         if (MODE == MODE_ADDX) {
-          float4 r = *reinterpret_cast<float4*>(rp);
-          r.x = fmaf(p.coef, xv[0], r.x); r.y = fmaf(p.coef, xv[1], r.y);
-          r.z = fmaf(p.coef, xv[2], r.z); r.w = fmaf(p.coef, xv[3], r.w);
-          *reinterpret_cast<float4*>(rp) = r;
+          ushort4 h = *rph, l = *rpl;
+          const float r0 = fmaf(p.coef, xv[0], join_f16x2(h.x, l.x)), r1 = fmaf(p.coef, xv[1], join_f16x2(h.y, l.y));
+          const float r2 = fmaf(p.coef, xv[2], join_f16x2(h.z, l.z)), r3 = fmaf(p.coef, xv[3], join_f16x2(h.w, l.w));
+          split_f16x2(r0, h.x, l.x); split_f16x2(r1, h.y, l.y); split_f16x2(r2, h.z, l.z); split_f16x2(r3, h.w, l.w);
+          *rph = h; *rpl = l;
         } else {
           float y[4];
           load_y4<YT>(reinterpret_cast<const YT*>(p.Y) + j * p.ldI + ig, y);
@@ -186,9 +189,11 @@ eta_rows_kernel(const EtaParams p) {
               if (lw < -745.13f) lw = -INFINITY;                  // exp() underflows to 0 in R's doubles
               tsyl = fmaf(y[a], lw, tsyl);
             }
-            rr[a] = y[a] - w;
+            rr[a] = (y[a] - w) * p.rscale;
           }
-          *reinterpret_cast<float4*>(rp) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+          ushort4 h, l;
+          split_f16x2(rr[0], h.x, l.x); split_f16x2(rr[1], h.y, l.y); split_f16x2(rr[2], h.z, l.z); split_f16x2(rr[3], h.w, l.w);
+          *rph = h; *rpl = l;
         }
       }
       if (MODE == MODE_FUSED) { sw += (double)tsw; syl += (double)tsyl; }
@@ -427,11 +432,11 @@ static void launch_fused(Ctx& ctx, const EtaParams& p, dim3 grid, size_t smem, b
 
 void pass_fused(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const Counts& y,
                 const float* f_row, const float* g_col, const float* la_row, const float* lb_col,
-                float maxY, float* resid, double* out3) {
+                float maxY, ResidBuf resid, double* out3) {
   EtaParams p;
   fill_params(p, g, x);
   p.f_row = f_row; p.g_col = g_col; p.la_row = la_row; p.lb_col = lb_col;
-  p.Y = y.data; p.R = resid; p.maxY = maxY; p.log_maxY = logf(maxY);
+  p.Y = y.data; p.Rhi = resid.hi; p.Rlo = resid.lo; p.rscale = resid.scale; p.maxY = maxY; p.log_maxY = logf(maxY);
   int nIt, nchunk, tpc;
   choose_chunks(ctx, g, nIt, nchunk, tpc);
   p.tiles_per_chunk = tpc;
@@ -457,11 +462,11 @@ void pass_fused(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const Co
   }
 }
 
-void pass_addx(Ctx& ctx, const PassGeom& g, const XDesc& x, float coef, float* resid) {
+void pass_addx(Ctx& ctx, const PassGeom& g, const XDesc& x, float coef, ResidBuf resid) {
   if (x.M == 0 || coef == 0.0f) return;
   EtaParams p;
   fill_params(p, g, x);
-  p.R = resid; p.coef = coef;
+  p.Rhi = resid.hi; p.Rlo = resid.lo; p.coef = coef * resid.scale;
   int nIt, nchunk, tpc;
   choose_chunks(ctx, g, nIt, nchunk, tpc);
   p.tiles_per_chunk = tpc;
@@ -480,7 +485,7 @@ void pass_addx(Ctx& ctx, const PassGeom& g, const XDesc& x, float coef, float* r
 }
 
 double fused_pass_bytes(const PassGeom& g, const XDesc& x, int y_elem_bytes) {
-  // N*s_Y (Y read) + 4N (fp32 residual write) + 4M(I+J) (factor tiles) + 8(I*nbatch + J) (alpha, beta)
+  // N*s_Y (Y read) + 4N (residual write: two fp16 planes) + 4M(I+J) (factor tiles) + 8(I*nbatch + J) (alpha, beta)
   const double N = (double)g.I * (double)g.J;
   return N * y_elem_bytes + 4.0 * N + 4.0 * x.M * ((double)g.I + (double)g.J) +
          8.0 * ((double)g.I * g.nbatch + (double)g.J);

@@ -4,6 +4,7 @@
 #pragma once
 #include "common.cuh"
 #include "counts.cuh"
+#include "products.cuh"
 
 namespace scgbm {
 
@@ -34,14 +35,14 @@ void pass_rowsum(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const f
 // C[j] = sum_i f_{i,b(j)} * exp(X_ij)               (R/fit.R:134)   -> C (J, fp64)
 void pass_colsum(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* f_row, double* C);
 
-// W = min(f_i g_j exp(X_ij), max.Y); resid = Y - W (fp32, ldI x J); scalars:
+// W = min(f_i g_j exp(X_ij), max.Y); resid = Y - W (fp16 hi/lo planes of resid.scale * (Y - W), ldI x J); scalars:
 // out[0] = sum W, out[1] = sum_{Y != 0} Y log W, out[2] = max W    (R/fit.R:136-151,321)
 void pass_fused(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const Counts& y,
                 const float* f_row, const float* g_col, const float* la_row, const float* lb_col,
-                float maxY, float* resid, double* out3);
+                float maxY, ResidBuf resid, double* out3);
 
 // resid += coef * X_ij   (iterations 1-2: the clamped, non-low-rank X0 terms of G)
-void pass_addx(Ctx& ctx, const PassGeom& g, const XDesc& x, float coef, float* resid);
+void pass_addx(Ctx& ctx, const PassGeom& g, const XDesc& x, float coef, ResidBuf resid);
 
 // algorithmic bytes of one fused-pass launch (SURVEY 8d / BASELINE.md section 4)
 double fused_pass_bytes(const PassGeom& g, const XDesc& x, int y_elem_bytes);

@@ -1,6 +1,6 @@
 // fit.cu -- K7: host control of gbm.sc's full-data fit (R/fit.R:76-211) over device
 // state.  X is never an I x J matrix: it is one of three factor slots; the only I x J
-// device objects are Y (compact counts) and the fp32 residual R.
+// device objects are Y (compact counts) and the residual R (two fp16 planes of the scaled residual, 4 B/entry).
 #include <chrono>
 #include "common.cuh"
 #include "counts.cuh"
@@ -96,20 +96,34 @@ __global__ void stage_factor_kernel(int64_t n_real, int64_t ld, int M, const dou
 }
 
 // Z = (Y - W0)/sqrt(W0) with W0 = a_i b_j:  z = y * s_i t_j - 1/(s_i t_j)    (R/fit.R:111-114)
-template <typename YT>
+// MAXONLY: only max |z| (as float bits, non-negative floats order like ints) -> zmax;
+// otherwise the fp16 planes of scale * z.
+template <typename YT, bool MAXONLY>
 __global__ void init_z_kernel(int64_t I, int64_t ldI, int64_t J, const YT* __restrict__ Y,
                               const float* __restrict__ s_row /* ldI x nbatch */, const float* __restrict__ t_col,
-                              const int32_t* __restrict__ batch, float* __restrict__ Z) {
+                              const int32_t* __restrict__ batch, float scale, uint16_t* __restrict__ Zhi,
+                              uint16_t* __restrict__ Zlo, int* __restrict__ zmax) {
   const int64_t j = blockIdx.y;
   const int kb = batch ? batch[j] : 0;
   const float tj = t_col[j];
+  float m = 0.0f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ldI; i += (int64_t)gridDim.x * blockDim.x) {
     float z = 0.0f;
     if (i < I) {
       const float st = s_row[(int64_t)kb * ldI + i] * tj;
       z = (float)Y[j * ldI + i] * st - 1.0f / st;
     }
-    Z[j * ldI + i] = z;
+    if (MAXONLY) {
+      m = fmaxf(m, fabsf(z));
+    } else {
+      uint16_t h, l;
+      split_f16x2(z * scale, h, l);
+      Zhi[j * ldI + i] = h; Zlo[j * ldI + i] = l;
+    }
+  }
+  if (MAXONLY) {
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(zmax, __float_as_int(m));
   }
 }
 
@@ -136,9 +150,10 @@ __global__ void write_w_kernel(int64_t I, int64_t ldI, int64_t j0, int64_t jc, i
   W[jl * I + i] = exp(alpha[(int64_t)kb * ldI + i] + x) * exp(beta[j]);
 }
 
-__global__ void f32_to_f64_kernel(int64_t n, const float* __restrict__ a, double* __restrict__ b) {
+__global__ void planes_to_f64_kernel(int64_t n, const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo,
+                                     double inv_scale, double* __restrict__ b) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) b[i] = (double)a[i];
+  if (i < n) b[i] = (double)join_f16x2(hi[i], lo[i]) * inv_scale;
 }
 
 __global__ void colsum_batch_total_kernel(int64_t I, int64_t ldI, int nbatch, const double* __restrict__ rowsum,
@@ -184,7 +199,9 @@ struct FitState {
   Counts Y;
   int64_t I, J, ldI, ldJ, J_total;
   int nbatch, M;
-  DevBuf<float> R;
+  DevBuf<uint16_t> Rhi, Rlo;          // residual planes (products.cuh)
+  float rscale = 1.0f;                // power-of-two scale of what the planes currently hold
+  ResidBuf resid() const { ResidBuf r; r.hi = Rhi.get(); r.lo = Rlo.get(); r.scale = rscale; return r; }
   DevBuf<double> alpha, beta, alpha0, beta0, logrs, logcs, S, Ccol, logtot, shift, scal;
   DevBuf<float> f_row, la_row, g_col, lb_col, s_row, t_col;
   Factor slot[3];
@@ -247,7 +264,7 @@ struct FitState {
     SCGBM_REQUIRE(M <= std::min(I, J_total), "M must not exceed min(nrow(Y), ncol(Y))");
     SCGBM_REQUIRE(maxY > 0.0, "Count matrix Y is all zero");
 
-    R.alloc(ldI * J);
+    Rhi.alloc(ldI * J); Rlo.alloc(ldI * J);
     alpha.alloc(ldI * nbatch); alpha0.alloc(ldI * nbatch); logrs.alloc(ldI * nbatch); S.alloc(ldI * nbatch);
     beta.alloc(ldJ); beta0.alloc(ldJ); logcs.alloc(ldJ); Ccol.alloc(ldJ);
     logtot.alloc(nbatch); shift.alloc(1);
@@ -295,26 +312,48 @@ struct FitState {
     SCGBM_LAUNCH_CHECK();
   }
 
+  template <bool MAXONLY>
+  void launch_init_z(float scale, int* zmax) {
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div(ldI, 256), 64), 1);
+    const int64_t slab = 65535;
+    for (int64_t j0 = 0; j0 < J; j0 += slab) {
+      grid.y = (unsigned)std::min(slab, J - j0);
+      const int32_t* bt = Y.batch.get() ? Y.batch.get() + j0 : nullptr;
+      uint16_t* zh = Rhi.get() + j0 * ldI; uint16_t* zl = Rlo.get() + j0 * ldI;
+      switch (Y.storage) {
+        case SCGBM_STORE_U8: init_z_kernel<uint8_t, MAXONLY><<<grid, 256, 0, ctx.stream>>>(I, ldI, J - j0, (const uint8_t*)Y.data + j0 * ldI, s_row.get(), t_col.get() + j0, bt, scale, zh, zl, zmax); break;
+        case SCGBM_STORE_U16: init_z_kernel<uint16_t, MAXONLY><<<grid, 256, 0, ctx.stream>>>(I, ldI, J - j0, (const uint16_t*)Y.data + j0 * ldI, s_row.get(), t_col.get() + j0, bt, scale, zh, zl, zmax); break;
+        default: init_z_kernel<float, MAXONLY><<<grid, 256, 0, ctx.stream>>>(I, ldI, J - j0, (const float*)Y.data + j0 * ldI, s_row.get(), t_col.get() + j0, bt, scale, zh, zl, zmax); break;
+      }
+      SCGBM_LAUNCH_CHECK();
+    }
+  }
+
   void init_svd() {
     {
-      ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
-      dim3 grid((unsigned)std::min<int64_t>(ceil_div(ldI, 256), 64), 1);
-      const int64_t slab = 65535;
-      for (int64_t j0 = 0; j0 < J; j0 += slab) {
-        grid.y = (unsigned)std::min(slab, J - j0);
-        const int32_t* bt = Y.batch.get() ? Y.batch.get() + j0 : nullptr;
-        float* z = R.get() + j0 * ldI;
-        switch (Y.storage) {
-          case SCGBM_STORE_U8: init_z_kernel<uint8_t><<<grid, 256, 0, ctx.stream>>>(I, ldI, J - j0, (const uint8_t*)Y.data + j0 * ldI, s_row.get(), t_col.get() + j0, bt, z); break;
-          case SCGBM_STORE_U16: init_z_kernel<uint16_t><<<grid, 256, 0, ctx.stream>>>(I, ldI, J - j0, (const uint16_t*)Y.data + j0 * ldI, s_row.get(), t_col.get() + j0, bt, z); break;
-          default: init_z_kernel<float><<<grid, 256, 0, ctx.stream>>>(I, ldI, J - j0, (const float*)Y.data + j0 * ldI, s_row.get(), t_col.get() + j0, bt, z); break;
-        }
-        SCGBM_LAUNCH_CHECK();
+      ProfScope ps(ctx.prof, SCGBM_K_MISC, 2);
+      // the planes are fp16: find max |Z| first so that the stored values stay in range
+      DevBuf<int> zmax(1);
+      zmax.zero(ctx.stream);
+      launch_init_z<true>(1.0f, zmax.get());
+      int bits = 0;
+      SCGBM_CUDA(cudaMemcpyAsync(&bits, zmax.get(), sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+      ctx.sync();
+      float zm;
+      memcpy(&zm, &bits, sizeof(float));
+      double h = zm;
+      if (ctx.nranks > 1) {          // every rank must use the same scale (the products are summed)
+        SCGBM_CUDA(cudaMemcpyAsync(scal.get() + 4, &h, sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+        ctx.allreduce_max(scal.get() + 4, 1);
+        SCGBM_CUDA(cudaMemcpyAsync(&h, scal.get() + 4, sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+        ctx.sync();
       }
+      rscale = resid_scale_for(h);
+      launch_init_z<false>(rscale, nullptr);
     }
     GOperator op;
     op.I = I; op.ldI = ldI; op.J = J; op.ldJ = ldJ; op.J_total = J_total;
-    op.R = R.get(); op.c = 1.0; op.nterms = 0;
+    op.R = resid(); op.c = 1.0; op.nterms = 0;
     TsvdOpts o = opts();
     Factor& f = slot[0];
     tsvd(ctx, svd, op, o, f.U.get(), f.d.get(), f.V.get(), nullptr, nullptr);     // R/fit.R:115
@@ -413,8 +452,14 @@ struct FitRun {
     }
     st.stage_cols();
     // (d)-(g) W, clip, objective, max W; residual Y - W           R/fit.R:136-151,321
+    {
+      // |Y - W| <= max.Y (W is clipped); in iterations 1-2 the clamped X0 (|x| <= 8) is folded
+      // into the planes with weight <= w.max / lr afterwards, so leave room for it
+      const bool x0 = fc.kind == XK_X0 || (prev >= 0 && prev != cur && st.slot[prev].kind == XK_X0);
+      st.rscale = resid_scale_for(st.maxY * (x0 ? 1.0 + 10.0 / std::min(lr, 1.0) : 1.0));
+    }
     pass_fused(ctx, st.eta, st.geom, xc, st.Y, st.f_row.get(), st.g_col.get(), st.la_row.get(), st.lb_col.get(),
-               (float)st.maxY, st.R.get(), st.scal.get());
+               (float)st.maxY, st.resid(), st.scal.get());
     if (fused_bytes == 0.0) {
       XDesc xm = xc; xm.M = M;
       fused_bytes = fused_pass_bytes(st.geom, xm, st.Y.elem_bytes());
@@ -466,13 +511,13 @@ struct FitRun {
     const double c = lr / w_max;                         // R/fit.R:321,323
     GOperator op;
     op.I = I; op.ldI = ldI; op.J = J; op.ldJ = ldJ; op.J_total = st.J_total;
-    op.R = st.R.get(); op.c = c; op.nterms = 0;
+    op.R = st.resid(); op.c = c; op.nterms = 0;
     auto add_term = [&](int s, double coef) {
       if (s < 0 || coef == 0.0) return;
       Factor& f = st.slot[s];
       if (f.kind == XK_ZERO) return;
       if (f.kind == XK_X0) {                             // clamped X0 is not low-rank: fold it into R
-        pass_addx(ctx, st.geom, st.desc(f), (float)(coef / c), st.R.get());
+        pass_addx(ctx, st.geom, st.desc(f), (float)(coef / c), st.resid());
         return;
       }
       LowRankTerm& t = op.t[op.nterms++];
@@ -629,6 +674,12 @@ void fit_impl(const scgbm_fit_args* a, scgbm_fit_out* out) {
 // ---------------------------------------------------------------------------------
 namespace scgbm {
 
+static double host_absmax(const float* x, int64_t n) {
+  double m = 0.0;
+  for (int64_t i = 0; i < n; ++i) m = std::max(m, (double)std::fabs(x[i]));
+  return m;
+}
+
 static void upload_padded(Ctx& ctx, const double* host, int64_t rows, int cols, int64_t ld, double* dev) {
   SCGBM_CUDA(cudaMemsetAsync(dev, 0, (size_t)ld * cols * sizeof(double), ctx.stream));
   SCGBM_CUDA(cudaMemcpy2DAsync(dev, ld * sizeof(double), host, rows * sizeof(double), rows * sizeof(double), cols,
@@ -646,7 +697,9 @@ void dbg_eval_impl(const scgbm_eval_args* a, scgbm_eval_out* out) {
   DevBuf<double> Xu(std::max<int64_t>(ldI * Mx, 1)), Xv(std::max<int64_t>(ldJ * Mx, 1)), alpha(ldI), beta(ldJ),
       logrs(ldI), logcs(ldJ), S(ldI), Cc(ldJ), shift(1), scal(4), tmp(std::max(ldI, ldJ));
   DevBuf<float> A32(std::max<int64_t>(ldI * Mx, 1)), B32(std::max<int64_t>(ldJ * Mx, 1)), f_row(ldI), la_row(ldI),
-      g_col(ldJ), lb_col(ldJ), rs32(ldI), cs32(ldJ), R(ldI * J);
+      g_col(ldJ), lb_col(ldJ), rs32(ldI), cs32(ldJ);
+  DevBuf<uint16_t> Rhi(ldI * J), Rlo(ldI * J);
+  ResidBuf R; R.hi = Rhi.get(); R.lo = Rlo.get(); R.scale = resid_scale_for(Y.maxY);
   alpha.zero(ctx.stream); beta.zero(ctx.stream);
   SCGBM_CUDA(cudaMemcpyAsync(beta.get(), a->beta_in, J * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
   XDesc x;
@@ -682,7 +735,7 @@ void dbg_eval_impl(const scgbm_eval_args* a, scgbm_eval_out* out) {
     beta_infer_kernel<<<GRID1(J)>>>(J, logcs.get(), Cc.get(), beta.get());
   }
   exp_stage_kernel<<<GRID1(ldJ)>>>(J, ldJ, 1, beta.get(), 1.0, g_col.get(), lb_col.get());
-  pass_fused(ctx, eta, geom, x, Y, f_row.get(), g_col.get(), la_row.get(), lb_col.get(), (float)Y.maxY, R.get(), scal.get());
+  pass_fused(ctx, eta, geom, x, Y, f_row.get(), g_col.get(), la_row.get(), lb_col.get(), (float)Y.maxY, R, scal.get());
   double h[3];
   SCGBM_CUDA(cudaMemcpyAsync(h, scal.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
   SCGBM_CUDA(cudaMemcpyAsync(out->alpha, alpha.get(), I * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
@@ -691,7 +744,7 @@ void dbg_eval_impl(const scgbm_eval_args* a, scgbm_eval_out* out) {
   out->sum_w = h[0]; out->sum_ylogw = h[1]; out->max_w = h[2]; out->max_Y = Y.maxY; out->LL = h[1] - h[0];
   if (out->resid) {
     DevBuf<double> Rd(ldI * J);
-    f32_to_f64_kernel<<<GRID1(ldI * J)>>>(ldI * J, R.get(), Rd.get());
+    planes_to_f64_kernel<<<GRID1(ldI * J)>>>(ldI * J, R.hi, R.lo, 1.0 / R.scale, Rd.get());
     SCGBM_LAUNCH_CHECK();
     SCGBM_CUDA(cudaMemcpy2DAsync(out->resid, I * sizeof(double), Rd.get(), ldI * sizeof(double), I * sizeof(double), J,
                                  cudaMemcpyDeviceToHost, ctx.stream));
@@ -708,12 +761,15 @@ void dbg_tsvd_impl(const scgbm_tsvd_args* a, scgbm_tsvd_out* out) {
   GOperator op;
   op.I = I; op.ldI = ldI; op.J = J; op.ldJ = ldJ; op.J_total = J;
   DevBuf<float> R;
+  DevBuf<uint16_t> Rhi, Rlo;
   if (a->R) {
-    R.alloc(ldI * J);
+    R.alloc(ldI * J); Rhi.alloc(ldI * J); Rlo.alloc(ldI * J);
     R.zero(ctx.stream);
     SCGBM_CUDA(cudaMemcpy2DAsync(R.get(), ldI * sizeof(float), a->R, I * sizeof(float), I * sizeof(float), J,
                                  cudaMemcpyHostToDevice, ctx.stream));
-    op.R = R.get(); op.c = a->c;
+    op.R.hi = Rhi.get(); op.R.lo = Rlo.get(); op.c = a->c;
+    op.R.scale = resid_scale_for(host_absmax(a->R, I * J));
+    split_planes(ctx, R.get(), ldI * J, op.R);
   }
   DevBuf<double> tA[2], td[2], tB[2];
   for (int t = 0; t < a->nterms; ++t) {
@@ -746,6 +802,65 @@ void dbg_tsvd_impl(const scgbm_tsvd_args* a, scgbm_tsvd_out* out) {
   ctx.sync();
   out->passes = passes;
   out->est = est;
+}
+
+void dbg_prod_impl(const scgbm_prod_args* a, scgbm_prod_out* out) {
+  SCGBM_REQUIRE(a && out && a->R && a->P && a->Q && out->outN && out->outT, "NULL args");
+  Ctx ctx(a->device, nullptr);
+  const int64_t I = a->I, J = a->J, ldI = round_up(I, kRowPad), ldJ = round_up(J, kRowPad);
+  const int b = a->b;
+  DevBuf<float> R(ldI * J);
+  DevBuf<uint16_t> Rhi(ldI * J), Rlo(ldI * J);
+  R.zero(ctx.stream);
+  SCGBM_CUDA(cudaMemcpy2DAsync(R.get(), ldI * sizeof(float), a->R, I * sizeof(float), I * sizeof(float), J,
+                               cudaMemcpyHostToDevice, ctx.stream));
+  ResidBuf rb; rb.hi = Rhi.get(); rb.lo = Rlo.get();
+  rb.scale = resid_scale_for(host_absmax(a->R, I * J));
+  split_planes(ctx, R.get(), ldI * J, rb);
+  DevBuf<double> P(ldJ * b), Q(ldI * b), oN(ldI * b), oT(ldJ * b);
+  upload_padded(ctx, a->P, J, b, ldJ, P.get());
+  upload_padded(ctx, a->Q, I, b, ldI, Q.get());
+  ProdWs ws;
+  const int reps = std::max(1, a->reps);
+  cudaEvent_t e0, e1;
+  SCGBM_CUDA(cudaEventCreate(&e0)); SCGBM_CUDA(cudaEventCreate(&e1));
+  float ms = 0;
+  for (int pass = 0; pass < 2; ++pass) {          // pass 0 warms up, pass 1 is timed
+    SCGBM_CUDA(cudaEventRecord(e0, ctx.stream));
+    for (int r = 0; r < (pass ? reps : 1); ++r) {
+      oN.zero(ctx.stream);
+      prod_n(ctx, ws, rb, I, ldI, J, P.get(), ldJ, b, a->c, oN.get(), ldI, a->variant);
+    }
+    SCGBM_CUDA(cudaEventRecord(e1, ctx.stream));
+    ctx.sync();
+    cudaEventElapsedTime(&ms, e0, e1);
+  }
+  out->ms_n = ms / reps;
+  for (int pass = 0; pass < 2; ++pass) {
+    SCGBM_CUDA(cudaEventRecord(e0, ctx.stream));
+    for (int r = 0; r < (pass ? reps : 1); ++r) {
+      oT.zero(ctx.stream);
+      prod_t(ctx, ws, rb, I, ldI, J, Q.get(), ldI, b, a->c, oT.get(), ldJ, a->variant);
+    }
+    SCGBM_CUDA(cudaEventRecord(e1, ctx.stream));
+    ctx.sync();
+    cudaEventElapsedTime(&ms, e0, e1);
+  }
+  out->ms_t = ms / reps;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  SCGBM_CUDA(cudaMemcpy2DAsync(out->outN, I * sizeof(double), oN.get(), ldI * sizeof(double), I * sizeof(double), b,
+                               cudaMemcpyDeviceToHost, ctx.stream));
+  SCGBM_CUDA(cudaMemcpy2DAsync(out->outT, J * sizeof(double), oT.get(), ldJ * sizeof(double), J * sizeof(double), b,
+                               cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  if (out->Rq) {
+    DevBuf<double> Rd(ldI * J);
+    planes_to_f64_kernel<<<GRID1(ldI * J)>>>(ldI * J, rb.hi, rb.lo, 1.0 / rb.scale, Rd.get());
+    SCGBM_LAUNCH_CHECK();
+    SCGBM_CUDA(cudaMemcpy2DAsync(out->Rq, I * sizeof(double), Rd.get(), ldI * sizeof(double), I * sizeof(double), J,
+                                 cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+  }
 }
 
 }  // namespace scgbm

@@ -1,4 +1,5 @@
-// products.cu -- K5, CUDA-core (FFMA) version of the tall-skinny residual products.
+// products.cu -- K5 dispatch + the CUDA-core (FFMA) version of the tall-skinny residual
+// products (validation path, and blocks wider than the tcgen05 kernel supports).
 // fp32 FMAs inside runs of <= 128 reduction steps, fp64 across runs, fixed-order
 // second stage for the split-K partials => bit-reproducible.
 #include "products.cuh"
@@ -6,6 +7,13 @@
 namespace scgbm {
 
 constexpr int PR_NT = 256;
+
+// four consecutive (scaled) residual entries from the two fp16 planes
+__device__ __forceinline__ float4 load_resid4(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, int64_t off) {
+  const ushort4 h = __ldg(reinterpret_cast<const ushort4*>(hi + off));
+  const ushort4 l = __ldg(reinterpret_cast<const ushort4*>(lo + off));
+  return make_float4(join_f16x2(h.x, l.x), join_f16x2(h.y, l.y), join_f16x2(h.z, l.z), join_f16x2(h.w, l.w));
+}
 
 // fp64 column-major (rows x b, ld) -> fp32 row-major (rows x bp), zero padded
 __global__ void to_f32_rowmajor(int64_t rows, int b, int bp, const double* __restrict__ src, int64_t ld,
@@ -30,7 +38,8 @@ static void convert_operand(Ctx& ctx, ProdWs& ws, int64_t rows, int b, int bp, c
 // ---------------------------------------------------------------------------------
 template <int BK>
 __global__ void __launch_bounds__(PR_NT, 2)
-prod_n_kernel(const float* __restrict__ R, int64_t ldI, int64_t J, const float* __restrict__ P, int bp,
+prod_n_kernel(const uint16_t* __restrict__ Rhi, const uint16_t* __restrict__ Rlo, int64_t ldI, int64_t J,
+              const float* __restrict__ P, int bp,
               int k0, int64_t cells_per_chunk, double* __restrict__ part) {
   constexpr int KT = BK / 8;            // column threads
   constexpr int GT = PR_NT / KT;        // gene threads
@@ -57,7 +66,7 @@ prod_n_kernel(const float* __restrict__ R, int64_t ldI, int64_t J, const float* 
       const int jj = idx / (TI / 4), q = idx % (TI / 4);
       const int64_t j = j0 + jj, i = i0 + 4 * q;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j < j_end && i < ldI) v = __ldg(reinterpret_cast<const float4*>(R + j * ldI + i));
+      if (j < j_end && i < ldI) v = load_resid4(Rhi, Rlo, j * ldI + i);
       *reinterpret_cast<float4*>(&As[jj][4 * q]) = v;
     }
     for (int idx = threadIdx.x; idx < KC * (BK / 4); idx += PR_NT) {
@@ -100,19 +109,35 @@ prod_n_kernel(const float* __restrict__ R, int64_t ldI, int64_t J, const float* 
 }
 
 __global__ void prod_n_reduce(int nchunk, int64_t ldI, int b, int bp, const double* __restrict__ part,
-                              double c, double* __restrict__ out, int64_t ldo) {
+                              double c, const float* __restrict__ c_dev, double* __restrict__ out, int64_t ldo) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= ldI * b) return;
   const int64_t i = idx % ldI;
   const int k = (int)(idx / ldI);
   double s = 0.0;
   for (int ch = 0; ch < nchunk; ++ch) s += part[((int64_t)ch * bp + k) * ldI + i];
-  out[(int64_t)k * ldo + i] += c * s;
+  out[(int64_t)k * ldo + i] += (c_dev ? c * (double)__ldg(c_dev) : c) * s;
 }
 
-void prod_n(Ctx& ctx, ProdWs& ws, const float* R, int64_t I, int64_t ldI, int64_t J, const double* P,
+void prod_n_reduce_launch(Ctx& ctx, int nchunk, int64_t ldI, int b, int bp, const double* part, double c,
+                          const float* c_dev, double* out, int64_t ldo) {
+  ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
+  prod_n_reduce<<<(unsigned)ceil_div(ldI * b, 256), 256, 0, ctx.stream>>>(nchunk, ldI, b, bp, part, c, c_dev, out, ldo);
+  SCGBM_LAUNCH_CHECK();
+}
+
+static bool use_tc(int variant, int b) {
+  if (variant == PROD_FFMA) return false;
+  if (variant == PROD_TCGEN05) { SCGBM_REQUIRE(prod_tc_supported(b), "tcgen05 products need a block of at most 64 columns"); return true; }
+  static const bool force_ffma = getenv("SCGBM_PROD_FFMA") != nullptr;
+  return !force_ffma && prod_tc_supported(b);
+}
+
+void prod_n(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t I, int64_t ldI, int64_t J, const double* P,
             int64_t ldP, int b, double c, double* out, int64_t ldo, int variant) {
-  (void)I; (void)variant;
+  (void)I;
+  c /= (double)R.scale;   // the planes hold scale * R
+  if (use_tc(variant, b)) { prod_n_tc(ctx, ws, R, ldI, J, P, ldP, b, c, out, ldo); return; }
   const int BK = b <= 32 ? 32 : 64;
   const int bp = (int)round_up(b, BK);
   convert_operand(ctx, ws, J, b, bp, P, ldP);
@@ -126,16 +151,12 @@ void prod_n(Ctx& ctx, ProdWs& ws, const float* R, int64_t I, int64_t ldI, int64_
     ProfScope ps(ctx.prof, SCGBM_K_PROD_N, bp / BK);
     dim3 grid(nIt, nchunk);
     for (int k0 = 0; k0 < bp; k0 += BK) {
-      if (BK == 32) prod_n_kernel<32><<<grid, PR_NT, 0, ctx.stream>>>(R, ldI, J, ws.op32.get(), bp, k0, cpc, ws.part.get());
-      else prod_n_kernel<64><<<grid, PR_NT, 0, ctx.stream>>>(R, ldI, J, ws.op32.get(), bp, k0, cpc, ws.part.get());
+      if (BK == 32) prod_n_kernel<32><<<grid, PR_NT, 0, ctx.stream>>>(R.hi, R.lo, ldI, J, ws.op32.get(), bp, k0, cpc, ws.part.get());
+      else prod_n_kernel<64><<<grid, PR_NT, 0, ctx.stream>>>(R.hi, R.lo, ldI, J, ws.op32.get(), bp, k0, cpc, ws.part.get());
       SCGBM_LAUNCH_CHECK();
     }
   }
-  {
-    ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
-    prod_n_reduce<<<(unsigned)ceil_div(ldI * b, 256), 256, 0, ctx.stream>>>(nchunk, ldI, b, bp, ws.part.get(), c, out, ldo);
-    SCGBM_LAUNCH_CHECK();
-  }
+  prod_n_reduce_launch(ctx, nchunk, ldI, b, bp, ws.part.get(), c, nullptr, out, ldo);
 }
 
 // ---------------------------------------------------------------------------------
@@ -144,7 +165,8 @@ void prod_n(Ctx& ctx, ProdWs& ws, const float* R, int64_t I, int64_t ldI, int64_
 // ---------------------------------------------------------------------------------
 template <int BK>
 __global__ void __launch_bounds__(PR_NT, 2)
-prod_t_kernel(const float* __restrict__ R, int64_t ldI, int64_t J, const float* __restrict__ Q, int bp,
+prod_t_kernel(const uint16_t* __restrict__ Rhi, const uint16_t* __restrict__ Rlo, int64_t ldI, int64_t J,
+              const float* __restrict__ Q, int bp,
               int k0, int b, double c, double* __restrict__ out, int64_t ldo) {
   constexpr int KT = BK / 8;
   constexpr int CT = PR_NT / KT;        // cell threads
@@ -167,7 +189,7 @@ prod_t_kernel(const float* __restrict__ R, int64_t ldI, int64_t J, const float* 
       const int cell = idx / (KC / 4), q = idx % (KC / 4);
       const int64_t j = j0 + cell;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j < J) v = __ldg(reinterpret_cast<const float4*>(R + j * ldI + i0 + 4 * q));
+      if (j < J) v = load_resid4(Rhi, Rlo, j * ldI + i0 + 4 * q);
       As[cell][4 * q + 0] = v.x; As[cell][4 * q + 1] = v.y;
       As[cell][4 * q + 2] = v.z; As[cell][4 * q + 3] = v.w;
     }
@@ -210,9 +232,11 @@ prod_t_kernel(const float* __restrict__ R, int64_t ldI, int64_t J, const float* 
   }
 }
 
-void prod_t(Ctx& ctx, ProdWs& ws, const float* R, int64_t I, int64_t ldI, int64_t J, const double* Q,
+void prod_t(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t I, int64_t ldI, int64_t J, const double* Q,
             int64_t ldQ, int b, double c, double* out, int64_t ldo, int variant) {
-  (void)I; (void)variant;
+  (void)I;
+  c /= (double)R.scale;
+  if (use_tc(variant, b)) { prod_t_tc(ctx, ws, R, ldI, J, Q, ldQ, b, c, out, ldo); return; }
   const int BK = b <= 32 ? 32 : 64;
   const int bp = (int)round_up(b, BK);
   convert_operand(ctx, ws, ldI, b, bp, Q, ldQ);   // Q has ldI rows (pad rows are zero)
@@ -220,8 +244,8 @@ void prod_t(Ctx& ctx, ProdWs& ws, const float* R, int64_t I, int64_t ldI, int64_
   ProfScope ps(ctx.prof, SCGBM_K_PROD_T, bp / BK);
   dim3 grid((unsigned)ceil_div(J, TJ));
   for (int k0 = 0; k0 < bp; k0 += BK) {
-    if (BK == 32) prod_t_kernel<32><<<grid, PR_NT, 0, ctx.stream>>>(R, ldI, J, ws.op32.get(), bp, k0, b, c, out, ldo);
-    else prod_t_kernel<64><<<grid, PR_NT, 0, ctx.stream>>>(R, ldI, J, ws.op32.get(), bp, k0, b, c, out, ldo);
+    if (BK == 32) prod_t_kernel<32><<<grid, PR_NT, 0, ctx.stream>>>(R.hi, R.lo, ldI, J, ws.op32.get(), bp, k0, b, c, out, ldo);
+    else prod_t_kernel<64><<<grid, PR_NT, 0, ctx.stream>>>(R.hi, R.lo, ldI, J, ws.op32.get(), bp, k0, b, c, out, ldo);
     SCGBM_LAUNCH_CHECK();
   }
 }

@@ -117,7 +117,7 @@ static void op_mul(Ctx& ctx, TsvdWs& ws, const GOperator& op, const double* P, i
     }
     ts_mul(ctx, op.ldI, lt.M, b, lt.A, lt.lda, C, lt.M, out, op.ldI, 1.0, 1.0);
   }
-  if (op.R && op.c != 0.0) prod_n(ctx, ws.prod, op.R, op.I, op.ldI, op.J, P, ldP, b, op.c, out, op.ldI, variant);
+  if (op.R.hi && op.c != 0.0) prod_n(ctx, ws.prod, op.R, op.I, op.ldI, op.J, P, ldP, b, op.c, out, op.ldI, variant);
   ctx.allreduce_sum(out, op.ldI * b);
 }
 
@@ -137,7 +137,7 @@ static void op_tmul(Ctx& ctx, TsvdWs& ws, const GOperator& op, const double* Q, 
     }
     ts_mul(ctx, op.J, lt.M, b, lt.B, lt.ldb, C, lt.M, out, op.ldJ, 1.0, 1.0);
   }
-  if (op.R && op.c != 0.0) prod_t(ctx, ws.prod, op.R, op.I, op.ldI, op.J, Q, ldQ, b, op.c, out, op.ldJ, variant);
+  if (op.R.hi && op.c != 0.0) prod_t(ctx, ws.prod, op.R, op.I, op.ldI, op.J, Q, ldQ, b, op.c, out, op.ldJ, variant);
 }
 
 static void tsvd_alloc(TsvdWs& ws, int64_t ldI, int64_t ldJ, int b, int pmax, int maxM) {

@@ -1,7 +1,7 @@
 // tsvd.cuh -- warm-started, restarted block-Krylov truncated SVD of the operator
 //     G = sum_t coef_t * A_t diag(d_t) B_t^T  +  c * R
-// (low-rank terms exact in fp64 through their factors, R the materialised fp32
-// residual).  Replaces irlba::irlba(V + (lr/w.max)(Y - W), nv = M) at R/fit.R:323 and
+// (low-rank terms exact in fp64 through their factors, R the materialised residual
+// in two bf16 planes).  Replaces irlba::irlba(V + (lr/w.max)(Y - W), nv = M) at R/fit.R:323 and
 // irlba::irlba(Z, nv = M) at R/fit.R:115.
 #pragma once
 #include "common.cuh"
@@ -21,7 +21,7 @@ struct LowRankTerm {
 struct GOperator {
   int64_t I = 0, ldI = 0, J = 0, ldJ = 0;
   int64_t J_total = 0;     // over all ranks
-  const float* R = nullptr;
+  ResidBuf R;              // bf16 hi/lo planes of the residual (R.hi == nullptr: no dense term)
   double c = 0.0;
   int nterms = 0;
   LowRankTerm t[2];
