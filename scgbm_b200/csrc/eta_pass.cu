@@ -276,6 +276,16 @@ scal_reduce_kernel(int64_t ncta, const double* __restrict__ part, double* __rest
   if (threadIdx.x == 0) { out[0] = s0[0]; out[1] = s1[0]; out[2] = s2[0]; out[3] = 0.0; }
 }
 
+void scal_reduce_launch(Ctx& ctx, int64_t ncta, const double* part, double* out3) {
+  scal_reduce_kernel<<<1, 1024, 0, ctx.stream>>>(ncta, part, out3);
+  SCGBM_LAUNCH_CHECK();
+}
+void rowpart_reduce_launch(Ctx& ctx, int nchunk, int64_t n, const double* part, double* S) {
+  ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
+  rowpart_reduce_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx.stream>>>(nchunk, n, part, S);
+  SCGBM_LAUNCH_CHECK();
+}
+
 // column sums (infer.beta): one CTA per cell tile, loops over all gene tiles -----
 template <bool MB>
 __global__ void __launch_bounds__(ET_NT, 2)

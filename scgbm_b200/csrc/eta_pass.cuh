@@ -8,6 +8,15 @@
 
 namespace scgbm {
 
+// tensor-core form of one side of X (eta_tc.cu): fp16 rows [rows_pad][Kp] holding the three
+// K sections of the scaled, two-piece factor; meta[1] = 1 / scale (device)
+struct Factor16 {
+  DevBuf<uint16_t> data;
+  DevBuf<float> meta;
+  int M = 0, Mp = 0, Kp = 0;
+  int64_t rows_pad = 0;
+};
+
 // X_ij = clamp?( rowscale?[i, b(j)] * sum_m A[i,m] B[j,m] )
 struct XDesc {
   const float* A = nullptr;   // ldI x M (col-major), d (and single-batch row scale) folded in
@@ -15,6 +24,8 @@ struct XDesc {
   int M = 0;                  // 0 -> X == 0
   int clamp = 0;              // clamp to [-8, 8]   (R/fit.R:119-120)
   const float* rowscale = nullptr;  // ldI x nbatch or null (multi-batch X0 only)
+  const Factor16* A16 = nullptr;    // genes (side 0) and cells (side 1) for the tcgen05 passes, or null
+  const Factor16* B16 = nullptr;
 };
 
 struct PassGeom {
@@ -43,6 +54,21 @@ void pass_fused(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const Co
 
 // resid += coef * X_ij   (iterations 1-2: the clamped, non-low-rank X0 terms of G)
 void pass_addx(Ctx& ctx, const PassGeom& g, const XDesc& x, float coef, ResidBuf resid);
+
+// ---- tcgen05 versions (eta_tc.cu): single batch, u8/u16 counts, M <= 64 -------------------
+bool eta_tc_supported(const PassGeom& g, const XDesc& x, int y_storage /* -1: pass without Y */);
+// side 0 = genes [hi|hi|lo], side 1 = cells [hi|lo|hi]; value = U[r,k] * d[k] * rs[r]
+void stage_factor16(Ctx& ctx, Factor16& f, int64_t n_real, int64_t ld, int M, int side, const double* U,
+                    const double* d, const float* rs);
+void pass_rowsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* g_col, double* S);
+// alpha/beta (fp64) and this rank's row sums of Y close the objective:
+//   sum_nz Y log W = sum Y x + sum_i alpha_i rs_i + sum_j beta_j cs_j   (+ clip correction)
+void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const Counts& y, const float* f_row,
+                   const float* g_col, const float* la_row, const float* lb_col, const double* alpha,
+                   const double* beta, const double* rowsum_local, float maxY, ResidBuf resid, double* out3);
+// fixed-order second stages shared by both implementations
+void scal_reduce_launch(Ctx& ctx, int64_t ncta, const double* part, double* out3);
+void rowpart_reduce_launch(Ctx& ctx, int nchunk, int64_t n, const double* part, double* S);
 
 // algorithmic bytes of one fused-pass launch (SURVEY 8d / BASELINE.md section 4)
 double fused_pass_bytes(const PassGeom& g, const XDesc& x, int y_elem_bytes);

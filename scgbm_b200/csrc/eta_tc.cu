@@ -1,0 +1,624 @@
+// eta_tc.cu -- K3/K4 on the 5th-generation tensor cores (single batch, u8/u16 counts).
+//
+// The eta tile X = A B^T (A: genes x M with d folded in, B: cells x M) comes out of tcgen05
+// UMMAs instead of 2M FFMAs per entry.  Each factor is scaled by a power of two and split in
+// two fp16 pieces (22 bits); the K dimension of the MMA is the concatenation of three
+// sections of Mp = round_up(M, 16) columns
+//         gene rows:  [ a_hi | a_hi | a_lo ]        cell rows:  [ b_hi | b_lo | b_hi ]
+// so that one accumulation gives a_hi b_hi + a_hi b_lo + a_lo b_hi = a.b to 2^-22 (every
+// fp16 x fp16 product is exact in fp32; alpha_i and beta_j stay OUT of the MMA so that the
+// truncating fp32 accumulator only ever sees |x|-sized partial sums).
+//
+//   fused_tc_kernel  (K4, R/fit.R:136-151,321,323): D[128 cells x 64 genes] in TMEM; epilogue
+//     thread = one cell (TMEM lane), 16 consecutive genes per tcgen05.ld chunk; Y tile arrives
+//     by TMA (128B swizzle: a thread's 32-byte run per chunk is conflict-free), the two fp16
+//     planes of scale*(Y - W) leave by TMA store from a double-buffered smem tile.
+//     sum W, sum_nz Y*x, max W are reduced fp32 per chunk -> fp64 per thread -> CTA partial;
+//     sum_nz Y log W = sum Y*x + sum_i alpha_i rs_i + sum_j beta_j cs_j (+ clip correction).
+//   rowsum_tc_kernel (K3, R/fit.R:127-130): D[128 genes x 128 cells]; epilogue thread = one
+//     gene, accumulates g_j exp(x_ij) over the cells; touches no I x J memory (SFU-bound).
+#include "eta_pass.cuh"
+#include "tc_common.cuh"
+
+namespace scgbm {
+
+// ---------------------------------------------------------------------------------
+// factor staging: fp64 (ld x M) [* d] [* rowscale] -> fp16 rows [ld_pad][Kp], three sections
+// ---------------------------------------------------------------------------------
+__global__ void factor_absmax_kernel(int64_t n_real, int64_t ld, int M, const double* __restrict__ U,
+                                     const double* __restrict__ d, const float* __restrict__ rs, int* __restrict__ out) {
+  float m = 0.0f;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_real * M; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx / n_real);
+    const int64_t r = idx % n_real;
+    const double v = U[(int64_t)k * ld + r] * (d ? d[k] : 1.0) * (rs ? (double)rs[r] : 1.0);
+    m = fmaxf(m, fabsf((float)v));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out, __float_as_int(m));
+}
+
+// side 0 (genes): [hi | hi | lo];  side 1 (cells): [hi | lo | hi];  rows >= n_real and columns >= M are zero
+__global__ void factor_stage16_kernel(int64_t n_real, int64_t rows_pad, int64_t ld, int M, int Mp, int Kp, int side,
+                                      const double* __restrict__ U, const double* __restrict__ d,
+                                      const float* __restrict__ rs, const int* __restrict__ absmax_bits,
+                                      uint16_t* __restrict__ out, float* __restrict__ inv_scale_out) {
+  const float mx = __int_as_float(*absmax_bits);
+  const float s = (mx > 0.0f && isfinite(mx)) ? exp2f(floorf(log2f(16384.0f / mx))) : 1.0f;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0) *inv_scale_out = 1.0f / s;
+  if (idx >= rows_pad * Mp) return;
+  const int64_t r = idx / Mp;
+  const int k = (int)(idx % Mp);
+  uint16_t hi = 0, lo = 0;
+  if (r < n_real && k < M) {
+    const double v = U[(int64_t)k * ld + r] * (d ? d[k] : 1.0) * (rs ? (double)rs[r] : 1.0);
+    split_f16x2((float)(v * (double)s), hi, lo);
+  }
+  uint16_t* row = out + r * Kp;
+  row[k] = hi;
+  row[Mp + k] = side == 0 ? hi : lo;
+  row[2 * Mp + k] = side == 0 ? lo : hi;
+  if (k == 0)
+    for (int z = 3 * Mp; z < Kp; ++z) row[z] = 0;
+}
+
+void stage_factor16(Ctx& ctx, Factor16& f, int64_t n_real, int64_t ld, int M, int side, const double* U,
+                    const double* d, const float* rs) {
+  f.M = M;
+  f.Mp = (int)round_up(M, 16);
+  f.Kp = (int)round_up(3 * f.Mp, 64);
+  f.rows_pad = round_up(ld, 128);
+  if (f.data.n < f.rows_pad * f.Kp) f.data.alloc(f.rows_pad * f.Kp);
+  if (f.meta.n < 2) f.meta.alloc(2);
+  int* absmax = reinterpret_cast<int*>(f.meta.get());
+  ProfScope ps(ctx.prof, SCGBM_K_MISC, 2);
+  SCGBM_CUDA(cudaMemsetAsync(absmax, 0, sizeof(int), ctx.stream));
+  factor_absmax_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_real * M, 256), 2048), 256, 0, ctx.stream>>>(n_real, ld, M, U, d, rs, absmax);
+  factor_stage16_kernel<<<(unsigned)ceil_div(f.rows_pad * f.Mp, 256), 256, 0, ctx.stream>>>(
+      n_real, f.rows_pad, ld, M, f.Mp, f.Kp, side, U, d, rs, absmax, f.data.get(), f.meta.get() + 1);
+  SCGBM_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------
+constexpr int FT_NT = 320;            // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int FT_EPI = 256;
+constexpr int FT_CELLS = 128;         // MMA M  (TMEM lanes = cells)
+constexpr int FT_GENES = 64;          // MMA N  (TMEM columns = genes)
+constexpr int FT_SLAB_A = FT_CELLS * 128;   // bytes of one 64-half K slab of the cell operand
+constexpr int FT_SLAB_B = FT_GENES * 128;
+constexpr int FT_R_BYTES = 2 * FT_CELLS * 128;   // hi + lo planes of one tile (each 128 rows x 128 B)
+
+struct FusedTcParams {
+  int64_t I, J, ldI;
+  int nslab, kk;                      // K slabs of 64 halves; UMMA K steps (3*Mp/16)
+  int n_cell_tiles, n_gene_tiles, gene_tiles_per_unit, n_units;
+  int y_stages, y_stage_bytes;
+  const float* f_row; const float* g_col;        // exp(alpha_i), exp(beta_j)   (padded, fp32)
+  const float* la_row; const float* lb_col;      // alpha_i, beta_j (fp32; clip correction only)
+  const float* inv_a; const float* inv_b;        // device: 1 / factor scales
+  float maxY, log_maxY, rscale;
+  double* scal_part;                  // [cta][4]
+};
+
+template <typename YT, bool CLAMP>
+__global__ void __launch_bounds__(FT_NT, 1)
+fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_constant__ CUtensorMap map_genes,
+                const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_hi,
+                const __grid_constant__ CUtensorMap map_lo, const FusedTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_buf = smem;                                          // nslab * 16 KB (cells)
+  uint8_t* b_buf = a_buf + p.nslab * FT_SLAB_A;                   // 2 * nslab * 8 KB (genes)
+  uint8_t* y_buf = b_buf + 2 * p.nslab * FT_SLAB_B;               // y_stages * y_stage_bytes
+  uint8_t* r_buf = y_buf + p.y_stages * p.y_stage_bytes;          // 2 * 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(r_buf + 2 * FT_R_BYTES);
+  uint64_t* a_full = bars;        uint64_t* a_empty = bars + 1;
+  uint64_t* b_full = bars + 2;    uint64_t* b_empty = bars + 4;   // [2]
+  uint64_t* d_full = bars + 6;    uint64_t* d_empty = bars + 8;   // [2]
+  uint64_t* y_full = bars + 10;   uint64_t* y_empty = bars + 14;  // [<=4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  double* red = reinterpret_cast<double*>(bars + 20);             // [8][4]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&map_cells); tc::tma_prefetch_desc(&map_genes); tc::tma_prefetch_desc(&map_y);
+    tc::tma_prefetch_desc(&map_hi); tc::tma_prefetch_desc(&map_lo);
+    tc::mbar_init(a_full, 1); tc::mbar_init(a_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1);
+      tc::mbar_init(&d_full[s], 1); tc::mbar_init(&d_empty[s], FT_EPI);
+    }
+    for (int s = 0; s < 4; ++s) { tc::mbar_init(&y_full[s], 1); tc::mbar_init(&y_empty[s], FT_EPI); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<128>(tmem_slot);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // unit -> (cell tile, first gene tile, gene tile count)
+  auto unit_info = [&](int unit, int& ct, int& gt0, int& ngt) {
+    const int chunks = (p.n_gene_tiles + p.gene_tiles_per_unit - 1) / p.gene_tiles_per_unit;
+    ct = unit / chunks;
+    gt0 = (unit % chunks) * p.gene_tiles_per_unit;
+    ngt = min(p.gene_tiles_per_unit, p.n_gene_tiles - gt0);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t bs = 0, bph = 0, ys = 0, yph = 0, aph = 0;
+      for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+        int ct, gt0, ngt;
+        unit_info(unit, ct, gt0, ngt);
+        tc::mbar_wait(a_empty, aph ^ 1);
+        tc::mbar_arrive_expect_tx(a_full, p.nslab * FT_SLAB_A);
+        for (int s = 0; s < p.nslab; ++s) tc::tma_load_2d(&map_cells, a_full, a_buf + s * FT_SLAB_A, s * 64, ct * FT_CELLS);
+        aph ^= 1;
+        for (int g = 0; g < ngt; ++g) {
+          const int gene0 = (gt0 + g) * FT_GENES;
+          tc::mbar_wait(&b_empty[bs], bph ^ 1);
+          tc::mbar_arrive_expect_tx(&b_full[bs], p.nslab * FT_SLAB_B);
+          for (int s = 0; s < p.nslab; ++s)
+            tc::tma_load_2d(&map_genes, &b_full[bs], b_buf + (bs * p.nslab + s) * FT_SLAB_B, s * 64, gene0);
+          if (++bs == 2) { bs = 0; bph ^= 1; }
+          tc::mbar_wait(&y_empty[ys], yph ^ 1);
+          tc::mbar_arrive_expect_tx(&y_full[ys], p.y_stage_bytes);
+          tc::tma_load_2d(&map_y, &y_full[ys], y_buf + ys * p.y_stage_bytes, gene0, ct * FT_CELLS);
+          if (++ys == (uint32_t)p.y_stages) { ys = 0; yph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = tc::instr_desc(0, 0, 0, 0, FT_CELLS, FT_GENES);
+      uint32_t bs = 0, bph = 0, db = 0, aph = 0;
+      uint32_t dph[2] = {0, 0};
+      for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+        int ct, gt0, ngt;
+        unit_info(unit, ct, gt0, ngt);
+        tc::mbar_wait(a_full, aph);
+        aph ^= 1;
+        for (int g = 0; g < ngt; ++g) {
+          tc::mbar_wait(&d_empty[db], dph[db] ^ 1);
+          tc::mbar_wait(&b_full[bs], bph);
+          tc::fence_after_sync();
+          const uint32_t a0 = tc::smem_u32(a_buf), b0 = tc::smem_u32(b_buf + bs * p.nslab * FT_SLAB_B);
+          const uint32_t d = tmem_base + db * FT_GENES;
+          for (int k = 0; k < p.kk; ++k) {
+            const uint64_t da = tc::smem_desc_sw128(a0 + (k >> 2) * FT_SLAB_A + (k & 3) * 32, 16, 1024);
+            const uint64_t dbd = tc::smem_desc_sw128(b0 + (k >> 2) * FT_SLAB_B + (k & 3) * 32, 16, 1024);
+            tc::mma_f16(d, da, dbd, idesc, k > 0 ? 1u : 0u);
+          }
+          tc::mma_commit(&b_empty[bs]);
+          tc::mma_commit(&d_full[db]);
+          if (g == ngt - 1) tc::mma_commit(a_empty);
+          dph[db] ^= 1; db ^= 1;
+          if (++bs == 2) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: one cell per thread, 2 chunks of 16 genes per tile =====
+    const int e = warp - 2;                 // 0..7
+    const int q = warp & 3;                 // TMEM lane quarter of this warp
+    const int ch = e >> 2;                  // column half: genes ch*32 .. ch*32+31 of the tile
+    const int row = q * 32 + lane;          // tile-local cell
+    const int et = threadIdx.x - 64;        // 0..255
+    const float inv = __ldg(p.inv_a) * __ldg(p.inv_b);
+    const float L_hi = 1.4426950216293335f * inv, L_lo = 1.9259629911e-08f * inv;   // log2(e) / (sA sB), split
+    const float clampv = 8.0f / inv;
+    double sw64 = 0.0, syl64 = 0.0;
+    float mw = 0.0f;
+    uint32_t ys = 0, yph = 0, db = 0, rb = 0;
+    uint32_t dph[2] = {0, 0};
+    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+      int ct, gt0, ngt;
+      unit_info(unit, ct, gt0, ngt);
+      const int64_t cell = (int64_t)ct * FT_CELLS + row;
+      const bool cell_ok = cell < p.J;
+      const float gj = cell_ok ? __ldg(p.g_col + cell) : 0.0f;
+      const float lbj = cell_ok ? __ldg(p.lb_col + cell) : 0.0f;
+      for (int g = 0; g < ngt; ++g) {
+        const int gene0 = (gt0 + g) * FT_GENES;
+        tc::mbar_wait(&d_full[db], dph[db]);
+        dph[db] ^= 1;
+        tc::mbar_wait(&y_full[ys], yph);
+        tc::fence_after_sync();
+        // the store that read r_buf[rb] two tiles ago must have drained it
+        if (et == 0) tc::tma_store_wait_read<1>();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const uint8_t* yt = y_buf + ys * p.y_stage_bytes;
+        uint8_t* rt = r_buf + rb * FT_R_BYTES;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col = ch * 32 + c * 16;            // first gene of the chunk within the tile
+          uint32_t xr[16];
+          tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + db * FT_GENES + col, xr);
+          float y[16];
+          if (sizeof(YT) == 2) {
+            const int q0 = col >> 3;                   // 16-byte chunk index (8 genes each)
+            const uint4 v0 = *reinterpret_cast<const uint4*>(yt + row * 128 + (((q0) ^ (row & 7)) << 4));
+            const uint4 v1 = *reinterpret_cast<const uint4*>(yt + row * 128 + (((q0 + 1) ^ (row & 7)) << 4));
+            const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { y[2 * k] = (float)(w[k] & 0xffffu); y[2 * k + 1] = (float)(w[k] >> 16); }
+          } else {
+            const uint4 v0 = *reinterpret_cast<const uint4*>(yt + row * 64 + col);
+            const uint32_t w[4] = {v0.x, v0.y, v0.z, v0.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              y[4 * k] = (float)(w[k] & 0xffu); y[4 * k + 1] = (float)((w[k] >> 8) & 0xffu);
+              y[4 * k + 2] = (float)((w[k] >> 16) & 0xffu); y[4 * k + 3] = (float)(w[k] >> 24);
+            }
+          }
+          float f[16];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 f4 = __ldg(reinterpret_cast<const float4*>(p.f_row + gene0 + col) + k);
+            f[4 * k] = f4.x; f[4 * k + 1] = f4.y; f[4 * k + 2] = f4.z; f[4 * k + 3] = f4.w;
+          }
+          tc::tmem_wait_ld();
+          float tsw = 0.0f, tsyl = 0.0f, cm = 0.0f;
+          float wv[16], r[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            float xs = __uint_as_float(xr[k]);                        // sA sB x
+            if (CLAMP) xs = fminf(fmaxf(xs, -clampv), clampv);        // R/fit.R:119-120
+            xr[k] = __float_as_uint(xs);
+            const float t = fmaf(xs, L_lo, xs * L_hi);
+            const float w = ex2_approx(t) * (f[k] * gj);
+            wv[k] = w;
+            cm = fmaxf(cm, w);
+            const float wc = fminf(w, p.maxY);                        // R/fit.R:145
+            tsw += wc;
+            tsyl = fmaf(y[k], xs, tsyl);                              // sum Y x (scaled)
+            r[k] = (y[k] - wc) * p.rscale;
+          }
+          double corr = 0.0;
+          if (cm > p.maxY) {   // rare: clipped entries take log(max.Y) instead of eta in the objective
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+              if (wv[k] > p.maxY && y[k] != 0.0f) {
+                const float lw = __uint_as_float(xr[k]) * inv + (__ldg(p.la_row + gene0 + col + k) + lbj);
+                corr += (double)y[k] * (double)(p.log_maxY - lw);
+              }
+          }
+          sw64 += (double)tsw;
+          syl64 += (double)tsyl * (double)inv + corr;
+          mw = fmaxf(mw, fminf(cm, p.maxY));
+          // fp16 planes, 16 genes = 32 bytes per plane: two 16-byte swizzled chunks
+          uint32_t hp[8], lp[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const __half2 h2 = __floats2half2_rn(r[2 * k], r[2 * k + 1]);
+            const float2 hf = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(r[2 * k] - hf.x, r[2 * k + 1] - hf.y);
+            hp[k] = *reinterpret_cast<const uint32_t*>(&h2);
+            lp[k] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
+          const int q0 = col >> 3;
+          uint8_t* rh = rt + row * 128;
+          uint8_t* rl = rt + FT_CELLS * 128 + row * 128;
+          *reinterpret_cast<uint4*>(rh + (((q0) ^ (row & 7)) << 4)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+          *reinterpret_cast<uint4*>(rh + (((q0 + 1) ^ (row & 7)) << 4)) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+          *reinterpret_cast<uint4*>(rl + (((q0) ^ (row & 7)) << 4)) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+          *reinterpret_cast<uint4*>(rl + (((q0 + 1) ^ (row & 7)) << 4)) = make_uint4(lp[4], lp[5], lp[6], lp[7]);
+        }
+        // TMEM buffer and Y stage are free again
+        tc::fence_before_sync();
+        tc::mbar_arrive(&d_empty[db]);
+        tc::mbar_arrive(&y_empty[ys]);
+        // hand the tile to the TMA store
+        tc::fence_proxy_async();
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (et == 0) {
+          tc::tma_store_2d(&map_hi, rt, gene0, ct * FT_CELLS);
+          tc::tma_store_2d(&map_lo, rt + FT_CELLS * 128, gene0, ct * FT_CELLS);
+          tc::tma_store_commit();
+        }
+        db ^= 1; rb ^= 1;
+        if (++ys == (uint32_t)p.y_stages) { ys = 0; yph ^= 1; }
+      }
+    }
+    if (et == 0) tc::tma_store_wait<0>();
+    // CTA partial of the three scalars (fixed order)
+    sw64 = warp_sum(sw64); syl64 = warp_sum(syl64); mw = warp_max(mw);
+    if (lane == 0) { red[e * 4 + 0] = sw64; red[e * 4 + 1] = syl64; red[e * 4 + 2] = (double)mw; }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (et == 0) {
+      double a = 0.0, b = 0.0, c = 0.0;
+      for (int w = 0; w < 8; ++w) { a += red[w * 4]; b += red[w * 4 + 1]; c = fmax(c, red[w * 4 + 2]); }
+      p.scal_part[(int64_t)blockIdx.x * 4 + 0] = a;
+      p.scal_part[(int64_t)blockIdx.x * 4 + 1] = b;
+      p.scal_part[(int64_t)blockIdx.x * 4 + 2] = c;
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) { tc::fence_after_sync(); tc::tmem_dealloc<128>(tmem_base); }
+}
+
+// out[1] += sum_i alpha_i rs_i + sum_j beta_j cs_j   (single CTA, fp64, fixed order)
+__global__ void __launch_bounds__(1024)
+ll_const_kernel(int64_t I, const double* __restrict__ alpha, const double* __restrict__ rs, int64_t J,
+                const double* __restrict__ beta, const double* __restrict__ cs, double* __restrict__ out) {
+  __shared__ double red[1024];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < I; i += 1024) s += alpha[i] * rs[i];
+  for (int64_t j = threadIdx.x; j < J; j += 1024) s += beta[j] * cs[j];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int st = 512; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[1] += red[0];
+}
+
+// ---------------------------------------------------------------------------------
+// K3 row sums:  S_i = sum_j g_j exp(x_ij);   D[128 genes x 128 cells], thread = gene
+// ---------------------------------------------------------------------------------
+constexpr int RT_NT = 320;
+constexpr int RT_TILE = 128;
+constexpr int RT_SLAB = RT_TILE * 128;
+
+struct RowsumTcParams {
+  int64_t J, ldI;
+  int nslab, kk;
+  int n_gene_tiles, n_chunks, cell_tiles_per_chunk, n_cell_tiles;
+  const float* g_col;
+  const float* inv_a; const float* inv_b;
+  double* row_part;     // [chunk][ldI]
+};
+
+template <bool CLAMP>
+__global__ void __launch_bounds__(RT_NT, 1)
+rowsum_tc_kernel(const __grid_constant__ CUtensorMap map_genes, const __grid_constant__ CUtensorMap map_cells,
+                 const RowsumTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_buf = smem;                                   // genes: nslab * 16 KB
+  uint8_t* b_buf = a_buf + p.nslab * RT_SLAB;              // cells: 2 * nslab * 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_buf + 2 * p.nslab * RT_SLAB);
+  uint64_t* a_full = bars;        uint64_t* a_empty = bars + 1;
+  uint64_t* b_full = bars + 2;    uint64_t* b_empty = bars + 4;
+  uint64_t* d_full = bars + 6;    uint64_t* d_empty = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* g_s = reinterpret_cast<float*>(bars + 12);        // [2][128] g_j of the cell tile in flight
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&map_genes); tc::tma_prefetch_desc(&map_cells);
+    tc::mbar_init(a_full, 1); tc::mbar_init(a_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1);
+      tc::mbar_init(&d_full[s], 1); tc::mbar_init(&d_empty[s], 256);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<256>(tmem_slot);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto unit_info = [&](int unit, int& gt, int& ct0, int& nct) {
+    gt = unit % p.n_gene_tiles;
+    const int chunk = unit / p.n_gene_tiles;
+    ct0 = chunk * p.cell_tiles_per_chunk;
+    nct = min(p.cell_tiles_per_chunk, p.n_cell_tiles - ct0);
+  };
+  const int n_units = p.n_gene_tiles * p.n_chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t bs = 0, bph = 0, aph = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        int gt, ct0, nct;
+        unit_info(unit, gt, ct0, nct);
+        tc::mbar_wait(a_empty, aph ^ 1);
+        tc::mbar_arrive_expect_tx(a_full, p.nslab * RT_SLAB);
+        for (int s = 0; s < p.nslab; ++s) tc::tma_load_2d(&map_genes, a_full, a_buf + s * RT_SLAB, s * 64, gt * RT_TILE);
+        aph ^= 1;
+        for (int c = 0; c < nct; ++c) {
+          tc::mbar_wait(&b_empty[bs], bph ^ 1);
+          tc::mbar_arrive_expect_tx(&b_full[bs], p.nslab * RT_SLAB);
+          for (int s = 0; s < p.nslab; ++s)
+            tc::tma_load_2d(&map_cells, &b_full[bs], b_buf + (bs * p.nslab + s) * RT_SLAB, s * 64, (ct0 + c) * RT_TILE);
+          if (++bs == 2) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::instr_desc(0, 0, 0, 0, RT_TILE, RT_TILE);
+      uint32_t bs = 0, bph = 0, db = 0, aph = 0;
+      uint32_t dph[2] = {0, 0};
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        int gt, ct0, nct;
+        unit_info(unit, gt, ct0, nct);
+        tc::mbar_wait(a_full, aph);
+        aph ^= 1;
+        for (int c = 0; c < nct; ++c) {
+          tc::mbar_wait(&d_empty[db], dph[db] ^ 1);
+          tc::mbar_wait(&b_full[bs], bph);
+          tc::fence_after_sync();
+          const uint32_t a0 = tc::smem_u32(a_buf), b0 = tc::smem_u32(b_buf + bs * p.nslab * RT_SLAB);
+          const uint32_t d = tmem_base + db * RT_TILE;
+          for (int k = 0; k < p.kk; ++k) {
+            const uint64_t da = tc::smem_desc_sw128(a0 + (k >> 2) * RT_SLAB + (k & 3) * 32, 16, 1024);
+            const uint64_t dbd = tc::smem_desc_sw128(b0 + (k >> 2) * RT_SLAB + (k & 3) * 32, 16, 1024);
+            tc::mma_f16(d, da, dbd, idesc, k > 0 ? 1u : 0u);
+          }
+          tc::mma_commit(&b_empty[bs]);
+          tc::mma_commit(&d_full[db]);
+          if (c == nct - 1) tc::mma_commit(a_empty);
+          dph[db] ^= 1; db ^= 1;
+          if (++bs == 2) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else {
+    const int e = warp - 2, q = warp & 3, ch = e >> 2;   // ch: cells ch*64 .. +63 of the tile
+    const int row = q * 32 + lane;                       // tile-local gene
+    const int et = threadIdx.x - 64;
+    const float inv = __ldg(p.inv_a) * __ldg(p.inv_b);
+    const float L_hi = 1.4426950216293335f * inv, L_lo = 1.9259629911e-08f * inv;
+    const float clampv = 8.0f / inv;
+    uint32_t db = 0;
+    uint32_t dph[2] = {0, 0};
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      int gt, ct0, nct;
+      unit_info(unit, gt, ct0, nct);
+      double s64 = 0.0;
+      for (int c = 0; c < nct; ++c) {
+        // stage g_j of this cell tile (double buffered with the TMEM accumulator)
+        if (et < RT_TILE) {
+          const int64_t cell = (int64_t)(ct0 + c) * RT_TILE + et;
+          g_s[db * RT_TILE + et] = cell < p.J ? __ldg(p.g_col + cell) : 0.0f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        tc::mbar_wait(&d_full[db], dph[db]);
+        dph[db] ^= 1;
+        tc::fence_after_sync();
+        float ts = 0.0f;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int col = ch * 64 + cc * 16;
+          uint32_t xr[16];
+          tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + db * RT_TILE + col, xr);
+          float gj[16];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 g4 = *reinterpret_cast<const float4*>(g_s + db * RT_TILE + col + 4 * k);
+            gj[4 * k] = g4.x; gj[4 * k + 1] = g4.y; gj[4 * k + 2] = g4.z; gj[4 * k + 3] = g4.w;
+          }
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            float xs = __uint_as_float(xr[k]);
+            if (CLAMP) xs = fminf(fmaxf(xs, -clampv), clampv);
+            ts = fmaf(ex2_approx(fmaf(xs, L_lo, xs * L_hi)), gj[k], ts);
+          }
+        }
+        s64 += (double)ts;
+        tc::fence_before_sync();
+        tc::mbar_arrive(&d_empty[db]);
+        db ^= 1;
+      }
+      // the two column halves of a gene meet in the fixed-order second stage: [chunk][half][ldI]
+      const int chunk = unit / p.n_gene_tiles;
+      const int64_t gene = (int64_t)gt * RT_TILE + row;
+      if (gene < p.ldI) p.row_part[((int64_t)chunk * 2 + ch) * p.ldI + gene] = s64;
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) { tc::fence_after_sync(); tc::tmem_dealloc<256>(tmem_base); }
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+bool eta_tc_supported(const PassGeom& g, const XDesc& x, int y_storage) {
+  static const bool off = getenv("SCGBM_ETA_FFMA") != nullptr;
+  if (off || g.nbatch != 1 || x.M < 1 || x.M > 64 || !x.A16 || !x.B16) return false;
+  if (y_storage >= 0 && y_storage != SCGBM_STORE_U8 && y_storage != SCGBM_STORE_U16) return false;
+  return true;
+}
+
+void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const Counts& y, const float* f_row,
+                   const float* g_col, const float* la_row, const float* lb_col, const double* alpha,
+                   const double* beta, const double* rowsum_local, float maxY, ResidBuf resid, double* out3) {
+  const Factor16& fa = *x.A16;
+  const Factor16& fb = *x.B16;
+  FusedTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.I = g.I; p.J = g.J; p.ldI = g.ldI;
+  p.nslab = fa.Kp / 64; p.kk = 3 * fa.Mp / 16;
+  p.n_cell_tiles = (int)ceil_div(g.J, FT_CELLS);
+  p.n_gene_tiles = (int)ceil_div(g.ldI, FT_GENES);
+  // enough units for ~16 per SM, at least 8 gene tiles each
+  int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div((int64_t)ctx.num_sms * 16, p.n_cell_tiles), p.n_gene_tiles / 8));
+  p.gene_tiles_per_unit = (int)ceil_div(p.n_gene_tiles, chunks);
+  chunks = (int)ceil_div(p.n_gene_tiles, p.gene_tiles_per_unit);
+  p.n_units = p.n_cell_tiles * chunks;
+  const int ybytes = y.elem_bytes();
+  p.y_stage_bytes = FT_CELLS * FT_GENES * ybytes;
+  const int fixed = p.nslab * FT_SLAB_A + 2 * p.nslab * FT_SLAB_B + 2 * FT_R_BYTES + 1024 + 512;
+  p.y_stages = std::min(4, (int)((225 * 1024 - fixed) / p.y_stage_bytes));
+  SCGBM_REQUIRE(p.y_stages >= 2, "fused_tc: not enough shared memory for this M");
+  const int smem_bytes = fixed + p.y_stages * p.y_stage_bytes;
+  p.f_row = f_row; p.g_col = g_col; p.la_row = la_row; p.lb_col = lb_col;
+  p.inv_a = fa.meta.get() + 1; p.inv_b = fb.meta.get() + 1;
+  p.maxY = maxY; p.log_maxY = logf(maxY); p.rscale = resid.scale;
+  const int grid = std::min(p.n_units, ctx.num_sms);
+  if (ws.scal_part.n < (int64_t)grid * 4) ws.scal_part.alloc((int64_t)grid * 4);
+  p.scal_part = ws.scal_part.get();
+  const CUtensorMap mc = make_tmap_2d(fb.data.get(), 2, false, (uint64_t)fb.Kp, (uint64_t)fb.rows_pad, (uint64_t)fb.Kp * 2, 64, FT_CELLS, 128);
+  const CUtensorMap mg = make_tmap_2d(fa.data.get(), 2, false, (uint64_t)fa.Kp, (uint64_t)fa.rows_pad, (uint64_t)fa.Kp * 2, 64, FT_GENES, 128);
+  const CUtensorMap my = make_tmap_2d(y.data, ybytes, false, (uint64_t)g.ldI, (uint64_t)g.J, (uint64_t)g.ldI * ybytes, FT_GENES, FT_CELLS,
+                                      ybytes == 2 ? 128 : 0);
+  const CUtensorMap mh = make_tmap_2d(resid.hi, 2, false, (uint64_t)g.ldI, (uint64_t)g.J, (uint64_t)g.ldI * 2, FT_GENES, FT_CELLS, 128);
+  const CUtensorMap ml = make_tmap_2d(resid.lo, 2, false, (uint64_t)g.ldI, (uint64_t)g.J, (uint64_t)g.ldI * 2, FT_GENES, FT_CELLS, 128);
+  {
+    ProfScope ps(ctx.prof, SCGBM_K_FUSED, 1);
+#define LAUNCH_FUSED(YT, CL)                                                                                          \
+  do {                                                                                                                \
+    SCGBM_CUDA(cudaFuncSetAttribute(fused_tc_kernel<YT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
+    fused_tc_kernel<YT, CL><<<grid, FT_NT, smem_bytes, ctx.stream>>>(mc, mg, my, mh, ml, p);                            \
+  } while (0)
+    if (ybytes == 2) { if (x.clamp) LAUNCH_FUSED(uint16_t, true); else LAUNCH_FUSED(uint16_t, false); }
+    else { if (x.clamp) LAUNCH_FUSED(uint8_t, true); else LAUNCH_FUSED(uint8_t, false); }
+#undef LAUNCH_FUSED
+    SCGBM_LAUNCH_CHECK();
+  }
+  {
+    ProfScope ps(ctx.prof, SCGBM_K_MISC, 2);
+    scal_reduce_launch(ctx, grid, ws.scal_part.get(), out3);
+    ll_const_kernel<<<1, 1024, 0, ctx.stream>>>(g.I, alpha, rowsum_local, g.J, beta, y.colsum.get(), out3);
+    SCGBM_LAUNCH_CHECK();
+  }
+}
+
+void pass_rowsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* g_col, double* S) {
+  const Factor16& fa = *x.A16;
+  const Factor16& fb = *x.B16;
+  RowsumTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.J = g.J; p.ldI = g.ldI;
+  p.nslab = fa.Kp / 64; p.kk = 3 * fa.Mp / 16;
+  p.n_gene_tiles = (int)ceil_div(g.ldI, RT_TILE);
+  p.n_cell_tiles = (int)ceil_div(g.J, RT_TILE);
+  int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div((int64_t)ctx.num_sms * 8, p.n_gene_tiles), ceil_div(p.n_cell_tiles, 4)));
+  p.cell_tiles_per_chunk = (int)ceil_div(p.n_cell_tiles, chunks);
+  p.n_chunks = (int)ceil_div(p.n_cell_tiles, p.cell_tiles_per_chunk);
+  p.g_col = g_col;
+  p.inv_a = fa.meta.get() + 1; p.inv_b = fb.meta.get() + 1;
+  const int64_t n = g.ldI;
+  if (ws.row_part.n < (int64_t)p.n_chunks * 2 * n) ws.row_part.alloc((int64_t)p.n_chunks * 2 * n);
+  p.row_part = ws.row_part.get();
+  const int smem_bytes = 3 * p.nslab * RT_SLAB + 1024 + 128 + 2 * RT_TILE * 4;
+  const int n_units = p.n_gene_tiles * p.n_chunks;
+  const int grid = std::min(n_units, ctx.num_sms);
+  const CUtensorMap mg = make_tmap_2d(fa.data.get(), 2, false, (uint64_t)fa.Kp, (uint64_t)fa.rows_pad, (uint64_t)fa.Kp * 2, 64, RT_TILE, 128);
+  const CUtensorMap mc = make_tmap_2d(fb.data.get(), 2, false, (uint64_t)fb.Kp, (uint64_t)fb.rows_pad, (uint64_t)fb.Kp * 2, 64, RT_TILE, 128);
+  {
+    ProfScope ps(ctx.prof, SCGBM_K_ROWSUM, 1);
+    if (x.clamp) {
+      SCGBM_CUDA(cudaFuncSetAttribute(rowsum_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      rowsum_tc_kernel<true><<<grid, RT_NT, smem_bytes, ctx.stream>>>(mg, mc, p);
+    } else {
+      SCGBM_CUDA(cudaFuncSetAttribute(rowsum_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      rowsum_tc_kernel<false><<<grid, RT_NT, smem_bytes, ctx.stream>>>(mg, mc, p);
+    }
+    SCGBM_LAUNCH_CHECK();
+  }
+  rowpart_reduce_launch(ctx, p.n_chunks * 2, n, ws.row_part.get(), S);
+}
+
+}  // namespace scgbm

@@ -16,6 +16,8 @@ struct Factor {
   int M = 0;
   DevBuf<double> U, d, V;      // ldI x M, M, ldJ x M   (orthonormal factors from the SVD)
   DevBuf<float> A32, B32;      // fp32 tiles for the eta passes: A32 = U d (* row scale), B32 = V (* col scale)
+  Factor16 a16, b16;           // the same, as fp16 tensor-core operands (single batch only)
+  bool has16 = false;
   void alloc(int64_t ldI, int64_t ldJ, int M_) {
     M = M_;
     U.alloc(ldI * M); d.alloc(M); V.alloc(ldJ * M); A32.alloc(ldI * M); B32.alloc(ldJ * M);
@@ -202,7 +204,7 @@ struct FitState {
   DevBuf<uint16_t> Rhi, Rlo;          // residual planes (products.cuh)
   float rscale = 1.0f;                // power-of-two scale of what the planes currently hold
   ResidBuf resid() const { ResidBuf r; r.hi = Rhi.get(); r.lo = Rlo.get(); r.scale = rscale; return r; }
-  DevBuf<double> alpha, beta, alpha0, beta0, logrs, logcs, S, Ccol, logtot, shift, scal;
+  DevBuf<double> alpha, beta, alpha0, beta0, logrs, logcs, S, Ccol, logtot, shift, scal, rs_local;
   DevBuf<float> f_row, la_row, g_col, lb_col, s_row, t_col;
   Factor slot[3];
   EtaWs eta;
@@ -216,6 +218,7 @@ struct FitState {
     XDesc x;
     if (f.kind == XK_ZERO) { x.M = 0; return x; }
     x.A = f.A32.get(); x.B = f.B32.get(); x.M = f.M;
+    if (f.has16) { x.A16 = &f.a16; x.B16 = &f.b16; }
     if (f.kind == XK_X0) {
       x.clamp = 1;
       x.rowscale = nbatch > 1 ? s_row.get() : nullptr;
@@ -240,6 +243,12 @@ struct FitState {
     stage_factor_kernel<<<GRID1(ldI * f.M)>>>(I, ldI, f.M, f.U.get(), f.d.get(), rs, f.A32.get());
     stage_factor_kernel<<<GRID1(ldJ * f.M)>>>(J, ldJ, f.M, f.V.get(), nullptr, cs, f.B32.get());
     SCGBM_LAUNCH_CHECK();
+    f.has16 = false;
+    if (nbatch == 1 && f.M <= 64) {
+      stage_factor16(ctx, f.a16, I, ldI, f.M, 0, f.U.get(), f.d.get(), rs);
+      stage_factor16(ctx, f.b16, J, ldJ, f.M, 1, f.V.get(), nullptr, cs);
+      f.has16 = true;
+    }
   }
 
   void setup() {
@@ -250,6 +259,8 @@ struct FitState {
     // global stats
     scal.alloc(8);
     double h[2] = {(double)J, Y.maxY};
+    rs_local.alloc(ldI * nbatch);     // this rank's row sums (the objective's constant term), before the all-reduce
+    SCGBM_CUDA(cudaMemcpyAsync(rs_local.get(), Y.rowsum.get(), ldI * nbatch * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
     if (ctx.nranks > 1) {
       SCGBM_CUDA(cudaMemcpyAsync(scal.get(), h, sizeof(h), cudaMemcpyHostToDevice, ctx.stream));
       ctx.allreduce_sum(scal.get(), 1);
@@ -434,7 +445,9 @@ struct FitRun {
     const double tr0 = trace ? now_sec() : 0.0;
     // (a) alphas <- log.rsy - log(rowSums(exp(X + betas)))      R/fit.R:127-130
     st.stage_cols();
-    pass_rowsum(ctx, st.eta, st.geom, xc, st.g_col.get(), st.S.get());
+    const bool tc_eta = eta_tc_supported(st.geom, xc, st.Y.storage);
+    if (tc_eta) pass_rowsum_tc(ctx, st.eta, st.geom, xc, st.g_col.get(), st.S.get());
+    else pass_rowsum(ctx, st.eta, st.geom, xc, st.g_col.get(), st.S.get());
     ctx.allreduce_sum(st.S.get(), ldI * nbatch);
     {
       ProfScope ps(ctx.prof, SCGBM_K_MISC, 2);
@@ -458,8 +471,12 @@ struct FitRun {
       const bool x0 = fc.kind == XK_X0 || (prev >= 0 && prev != cur && st.slot[prev].kind == XK_X0);
       st.rscale = resid_scale_for(st.maxY * (x0 ? 1.0 + 10.0 / std::min(lr, 1.0) : 1.0));
     }
-    pass_fused(ctx, st.eta, st.geom, xc, st.Y, st.f_row.get(), st.g_col.get(), st.la_row.get(), st.lb_col.get(),
-               (float)st.maxY, st.resid(), st.scal.get());
+    if (tc_eta)
+      pass_fused_tc(ctx, st.eta, st.geom, xc, st.Y, st.f_row.get(), st.g_col.get(), st.la_row.get(), st.lb_col.get(),
+                    st.alpha.get(), st.beta.get(), st.rs_local.get(), (float)st.maxY, st.resid(), st.scal.get());
+    else
+      pass_fused(ctx, st.eta, st.geom, xc, st.Y, st.f_row.get(), st.g_col.get(), st.la_row.get(), st.lb_col.get(),
+                 (float)st.maxY, st.resid(), st.scal.get());
     if (fused_bytes == 0.0) {
       XDesc xm = xc; xm.M = M;
       fused_bytes = fused_pass_bytes(st.geom, xm, st.Y.elem_bytes());
@@ -703,6 +720,7 @@ void dbg_eval_impl(const scgbm_eval_args* a, scgbm_eval_out* out) {
   alpha.zero(ctx.stream); beta.zero(ctx.stream);
   SCGBM_CUDA(cudaMemcpyAsync(beta.get(), a->beta_in, J * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
   XDesc x;
+  Factor16 a16, b16;
   if (Mx > 0) {
     upload_padded(ctx, a->Xu, I, Mx, ldI, Xu.get());
     upload_padded(ctx, a->Xv, J, Mx, ldJ, Xv.get());
@@ -721,12 +739,19 @@ void dbg_eval_impl(const scgbm_eval_args* a, scgbm_eval_out* out) {
     stage_factor_kernel<<<GRID1(ldJ * Mx)>>>(J, ldJ, Mx, Xv.get(), nullptr, cs, B32.get());
     SCGBM_LAUNCH_CHECK();
     x.A = A32.get(); x.B = B32.get(); x.M = Mx; x.clamp = a->clamp8;
+    if (Mx <= 64) {
+      stage_factor16(ctx, a16, I, ldI, Mx, 0, Xu.get(), nullptr, rs);
+      stage_factor16(ctx, b16, J, ldJ, Mx, 1, Xv.get(), nullptr, cs);
+      x.A16 = &a16; x.B16 = &b16;
+    }
   }
+  const bool tc_eta = eta_tc_supported(geom, x, Y.storage);
   EtaWs eta;
   log_kernel<<<GRID1(J)>>>(J, Y.colsum.get(), logcs.get());
   log_kernel<<<GRID1(ldI)>>>(ldI, Y.rowsum.get(), logrs.get());
   exp_stage_kernel<<<GRID1(ldJ)>>>(J, ldJ, 1, beta.get(), 1.0, g_col.get(), lb_col.get());
-  pass_rowsum(ctx, eta, geom, x, g_col.get(), S.get());
+  if (tc_eta) pass_rowsum_tc(ctx, eta, geom, x, g_col.get(), S.get());
+  else pass_rowsum(ctx, eta, geom, x, g_col.get(), S.get());
   alpha_update_kernel<<<1, 1024, 0, ctx.stream>>>(I, ldI, 1, logrs.get(), S.get(), nullptr, alpha.get(), shift.get());
   beta_shift_kernel<<<GRID1(J)>>>(J, beta.get(), shift.get());
   exp_stage_kernel<<<GRID1(ldI)>>>(I, ldI, 1, alpha.get(), 1.0, f_row.get(), la_row.get());
@@ -735,7 +760,11 @@ void dbg_eval_impl(const scgbm_eval_args* a, scgbm_eval_out* out) {
     beta_infer_kernel<<<GRID1(J)>>>(J, logcs.get(), Cc.get(), beta.get());
   }
   exp_stage_kernel<<<GRID1(ldJ)>>>(J, ldJ, 1, beta.get(), 1.0, g_col.get(), lb_col.get());
-  pass_fused(ctx, eta, geom, x, Y, f_row.get(), g_col.get(), la_row.get(), lb_col.get(), (float)Y.maxY, R, scal.get());
+  if (tc_eta)
+    pass_fused_tc(ctx, eta, geom, x, Y, f_row.get(), g_col.get(), la_row.get(), lb_col.get(), alpha.get(), beta.get(),
+                  Y.rowsum.get(), (float)Y.maxY, R, scal.get());
+  else
+    pass_fused(ctx, eta, geom, x, Y, f_row.get(), g_col.get(), la_row.get(), lb_col.get(), (float)Y.maxY, R, scal.get());
   double h[3];
   SCGBM_CUDA(cudaMemcpyAsync(h, scal.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
   SCGBM_CUDA(cudaMemcpyAsync(out->alpha, alpha.get(), I * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));

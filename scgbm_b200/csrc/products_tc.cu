@@ -279,7 +279,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 CUtensorMap make_tmap_2d(const void* base, int elem_bytes, bool is_float, uint64_t inner, uint64_t outer,
-                         uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+                         uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -299,7 +299,7 @@ CUtensorMap make_tmap_2d(const void* base, int elem_bytes, bool is_float, uint64
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(&m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char b[256];

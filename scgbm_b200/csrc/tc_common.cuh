@@ -10,9 +10,9 @@ namespace scgbm {
 
 // ---- host: CUtensorMap for a 2-D row-of-`inner` tensor of 16-bit / 32-bit elements -------
 // dims = {inner (contiguous), outer}; stride of `outer` in bytes; box = {box_inner, box_outer};
-// 128-byte swizzle (box_inner * elem_bytes must be <= 128).
+// swizzle_bytes = 128 (box_inner * elem_bytes must be <= 128) or 0 (dense rows).
 CUtensorMap make_tmap_2d(const void* base, int elem_bytes, bool is_float, uint64_t inner, uint64_t outer,
-                         uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+                         uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes = 128);
 
 #ifdef __CUDACC__
 namespace tc {

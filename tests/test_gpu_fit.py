@@ -96,7 +96,8 @@ def test_storage_formats_agree(storage, dtype):
     Y = np.minimum(_sim(200, 300, 4, seed=11), 255)
     base = gbm_sc(Y.astype(np.int32), 4, diagnostics=True, max_iter=15, y_storage=2)
     out = gbm_sc(Y.astype(dtype), 4, diagnostics=True, max_iter=15, y_storage=storage)
-    np.testing.assert_allclose(out["_LL"], base["_LL"], rtol=1e-12)
+    # u8 / u16 run the same tcgen05 kernels -> identical sums; f32 storage takes the CUDA-core kernels
+    np.testing.assert_allclose(out["_LL"], base["_LL"], rtol=1e-12 if storage != 3 else 2e-7)
     assert out["_y_storage"] == (storage if storage else 2)
 
 
