@@ -176,7 +176,8 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
   // keep the Krylov basis inside the space: b * (depth + 1) <= min(I, J)
   const int depth_cap = (int)std::max<int64_t>(0, minIJ / b - 1);
   const int depth_warm = std::min(std::max(0, o.depth), depth_cap);
-  const int depth_cold = std::min(std::max(depth_warm, o.cold_depth), depth_cap);
+  static const int env_cold = getenv("SCGBM_COLD_DEPTH") ? atoi(getenv("SCGBM_COLD_DEPTH")) : -1;
+  const int depth_cold = std::min(std::max(depth_warm, env_cold >= 0 ? env_cold : o.cold_depth), depth_cap);
   const int64_t ldI = op.ldI, ldJ = op.ldJ;
   int maxM = 1;
   for (int t = 0; t < op.nterms; ++t) maxM = std::max(maxM, op.t[t].M);
@@ -187,7 +188,9 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
 
   int passes = 0;
   double est = 1e300;
-  bool robust = ws.robust;
+  // a cold start runs many restarted cycles whose late Krylov blocks are nearly dependent on the
+  // converged directions: orthonormalise through the eigen-decomposition from the start there
+  bool robust = ws.robust || !was_warm;
   for (int attempt = 0; attempt < 2; ++attempt) {
     bool restart = false;
     ws.flag.zero(ctx.stream);
@@ -224,7 +227,8 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
         // the first block (the estimate cannot be small there), every block when warm,
         // every other block on a cold start, and always at the end of the cycle
         const bool last = t >= depth;
-        const bool check = last || (t >= 1 && (was_warm || (t % 2 == 1)));
+        // (the p x p Jacobi eigensolve is the expensive part of a cold cycle: only at its end)
+        const bool check = last || (t >= 1 && was_warm);
         if (check) {
           {
             ProfScope ps(ctx.prof, SCGBM_K_SMALL, 1);
@@ -261,6 +265,8 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
       }
       ts_mul(ctx, ldI, p, b, ws.Qb.get(), ldI, ws.S.get(), p, ws.Ub.get(), ldI, 1.0, 0.0);
       ts_mul(ctx, op.J, p, b, ws.Zb.get(), ldJ, ws.C.get(), p, ws.Vwarm.get(), ldJ, 1.0, 0.0);
+      static const bool trace = getenv("SCGBM_TRACE") != nullptr;
+      if (trace) fprintf(stderr, "[scgbm-trace]   tsvd %s cycle %d: p=%d passes so far %d est %.3e\n", was_warm ? "warm" : "cold", cycle, p, passes, est);
       const bool converged = est < o.tol || depth == 0;
       if (converged || cycle + 1 >= o.max_cycles || (was_warm && cycle >= 1)) break;
       V0 = ws.Vwarm.get();
