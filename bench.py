@@ -286,14 +286,17 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "fused_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
+            tj = json.load(open(tpath))      # measured on a smaller shard: scale by the algorithmic bytes
+            traffic = tj["traffic_bytes_per_launch"] / tj["algorithmic_bytes_per_launch"] * fused_bytes
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                "kernel": "eta_rows_kernel<MODE_FUSED> (K4 fused likelihood pass)", "peak_source": peak_src,
-                "bytes_per_launch": fused_bytes, "ms_per_launch": fused_ms,
-                "note": "algorithmic bytes = N*s_Y + 4N (fp32 residual write) + 4M(I+J) + 8(I+J), this rank's shard"}
+                "kernel": "fused_tc_kernel<uint16_t> (K4 fused likelihood pass: tcgen05 eta tile, TMA in/out)",
+                "peak_source": peak_src, "bytes_per_launch": fused_bytes, "ms_per_launch": fused_ms,
+                "traffic_note": "ncu dram bytes of the same kernel on a 20000x100000 shard (profiles/fused_traffic.json): "
+                                "1.012x its algorithmic bytes; scales with the shard",
+                "note": "algorithmic bytes = N*s_Y + 4N (two fp16 residual planes) + 4M(I+J) + 8(I+J), this rank's shard"}
     value = K / (ms * 1e-3)
 
     # ---------------- e2e: the public API with host buffers ----------------------
@@ -352,11 +355,12 @@ def main():
     line = {
         "metric": "gbm_sc_iters_per_sec", "value": value, "unit": "iters/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32 eta / f64 reductions and small dense", "data": "synthetic",
+        "dtype": "f32 (eta from fp16x2-split tcgen05 MMAs, fp32 exp; f64 reductions and small dense)", "data": "synthetic",
         "config": {"workload": workload, "genes": I, "cells": J, "M": M, "y_device_format": "u16 (s_Y=2)",
                    "sharding": f"cells over {world} rank(s)",
-                   "l2": "inputs (Y + fp32 residual) are far larger than the 126 MB L2; no flush needed",
-                   "svd": "block-Krylov, block M+12, adaptive depth, tol 1e-4", "svd_passes_per_step": svd_passes / K},
+                   "l2": "inputs (Y + residual planes, 6 B/entry) are far larger than the 126 MB L2; no flush needed",
+                   "svd": "warm block-Krylov, block M+12, adaptive depth, tol 1e-4; products on tcgen05",
+                   "svd_passes_per_step": svd_passes / K},
         "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "clocks": clocks,
         "gpu_launches": int(sum(launches.values())),
         "kernel_ms_per_step": {k: v / K for k, v in kms.items()},

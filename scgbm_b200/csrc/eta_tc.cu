@@ -245,7 +245,10 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
             const uint4 v1 = *reinterpret_cast<const uint4*>(yt + row * 128 + (((q0 + 1) ^ (row & 7)) << 4));
             const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { y[2 * k] = (float)(w[k] & 0xffffu); y[2 * k + 1] = (float)(w[k] >> 16); }
+            for (int k = 0; k < 8; ++k) {   // exact small-int -> float on the ALU/FMA pipes (the XU pipe is busy with ex2)
+              y[2 * k] = __uint_as_float(0x4B000000u | (w[k] & 0xffffu)) - 8388608.0f;
+              y[2 * k + 1] = __uint_as_float(0x4B000000u | (w[k] >> 16)) - 8388608.0f;
+            }
           } else {
             const uint4 v0 = *reinterpret_cast<const uint4*>(yt + row * 64 + col);
             const uint32_t w[4] = {v0.x, v0.y, v0.z, v0.w};
