@@ -134,10 +134,10 @@ static bool use_tc(int variant, int b) {
 }
 
 void prod_n(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t I, int64_t ldI, int64_t J, const double* P,
-            int64_t ldP, int b, double c, double* out, int64_t ldo, int variant) {
+            int64_t ldP, int b, double c, double* out, int64_t ldo, int variant, bool use_lo) {
   (void)I;
   c /= (double)R.scale;   // the planes hold scale * R
-  if (use_tc(variant, b)) { prod_n_tc(ctx, ws, R, ldI, J, P, ldP, b, c, out, ldo); return; }
+  if (use_tc(variant, b)) { prod_n_tc(ctx, ws, R, ldI, J, P, ldP, b, c, out, ldo, use_lo); return; }
   const int BK = b <= 32 ? 32 : 64;
   const int bp = (int)round_up(b, BK);
   convert_operand(ctx, ws, J, b, bp, P, ldP);

@@ -47,8 +47,11 @@ struct ProdWs {
 
 enum { PROD_AUTO = 0, PROD_FFMA = 1, PROD_TCGEN05 = 2 };
 
+// use_lo = false: the tcgen05 kernel reads only the hi plane (11-bit residual, half the bytes) --
+// good enough for passes that merely build a Krylov basis; every pass whose output enters the
+// Rayleigh-Ritz projection (prod_t) keeps both planes.
 void prod_n(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t I, int64_t ldI, int64_t J, const double* P,
-            int64_t ldP, int b, double c, double* out, int64_t ldo, int variant);
+            int64_t ldP, int b, double c, double* out, int64_t ldo, int variant, bool use_lo = true);
 
 void prod_t(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t I, int64_t ldI, int64_t J, const double* Q,
             int64_t ldQ, int b, double c, double* out, int64_t ldo, int variant);
@@ -56,7 +59,7 @@ void prod_t(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t I, int64_t ldI, int64_t J,
 // tcgen05 implementations (products_tc.cu); b <= 64
 bool prod_tc_supported(int b);
 void prod_n_tc(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t ldI, int64_t J, const double* P, int64_t ldP,
-               int b, double c, double* out, int64_t ldo);
+               int b, double c, double* out, int64_t ldo, bool use_lo);
 void prod_t_tc(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t ldI, int64_t J, const double* Q, int64_t ldQ,
                int b, double c, double* out, int64_t ldo);
 void prod_n_reduce_launch(Ctx& ctx, int nchunk, int64_t ldI, int b, int bp, const double* part, double c,

@@ -44,6 +44,7 @@ struct TcParams {
   int64_t ldo;
   int b;
   uint32_t a_lbo, a_sbo;     // N-mode A descriptor strides (bytes)
+  int use_lo;                // 0: hi plane only (basis-building passes; 11-bit residual)
 };
 
 template <int BP, bool TRANS>
@@ -94,21 +95,25 @@ prod_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
           tc::mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* a_hi = st; uint8_t* a_lo = st + TC_PLANE_BYTES; uint8_t* bt = st + 2 * TC_PLANE_BYTES;
-          tc::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          tc::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES - (p.use_lo ? 0 : TC_PLANE_BYTES));
           if (!TRANS) {
             const int cell = (int)(c0 + (int64_t)kb * TC_KB);
             tc::tma_load_2d(&map_hi, &full[stage], a_hi, gene0, cell);
             tc::tma_load_2d(&map_hi, &full[stage], a_hi + TC_PLANE_BYTES / 2, gene0 + 64, cell);
-            tc::tma_load_2d(&map_lo, &full[stage], a_lo, gene0, cell);
-            tc::tma_load_2d(&map_lo, &full[stage], a_lo + TC_PLANE_BYTES / 2, gene0 + 64, cell);
+            if (p.use_lo) {
+              tc::tma_load_2d(&map_lo, &full[stage], a_lo, gene0, cell);
+              tc::tma_load_2d(&map_lo, &full[stage], a_lo + TC_PLANE_BYTES / 2, gene0 + 64, cell);
+            }
             tc::tma_load_2d(&map_b, &full[stage], bt, cell, 0);
           } else {
             const int gene = kb * TC_KB;
             const int cell0 = (int)c0;
             tc::tma_load_2d(&map_hi, &full[stage], a_hi, gene, cell0);
             tc::tma_load_2d(&map_hi, &full[stage], a_hi + TC_PLANE_BYTES / 2, gene, cell0 + 64);
-            tc::tma_load_2d(&map_lo, &full[stage], a_lo, gene, cell0);
-            tc::tma_load_2d(&map_lo, &full[stage], a_lo + TC_PLANE_BYTES / 2, gene, cell0 + 64);
+            if (p.use_lo) {
+              tc::tma_load_2d(&map_lo, &full[stage], a_lo, gene, cell0);
+              tc::tma_load_2d(&map_lo, &full[stage], a_lo + TC_PLANE_BYTES / 2, gene, cell0 + 64);
+            }
             tc::tma_load_2d(&map_b, &full[stage], bt, gene, 0);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -146,7 +151,7 @@ prod_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
             }
             const uint64_t db = tc::smem_desc_sw128(bt + ks * 32, 16, 1024);
             tc::mma_f16(d, da_hi, db, idesc_hi, (kd > 0 || ks > 0) ? 1u : 0u);
-            tc::mma_f16(d, da_lo, db, idesc_lo, 1u);
+            if (p.use_lo) tc::mma_f16(d, da_lo, db, idesc_lo, 1u);
           }
           tc::mma_commit(&empty[stage]);
           if (kd == TC_DRAIN - 1 || kb == nkb - 1) {
@@ -346,7 +351,7 @@ static void split_operand(Ctx& ctx, ProdWs& ws, int64_t rows, int b, int bp, int
 }
 
 void prod_n_tc(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t ldI, int64_t J, const double* P, int64_t ldP,
-               int b, double c, double* out, int64_t ldo) {
+               int b, double c, double* out, int64_t ldo, bool use_lo) {
   SCGBM_REQUIRE(prod_tc_supported(b), "prod_n_tc: block too wide");
   const int bp = b <= 32 ? 32 : 64;
   const int64_t ldk = round_up(J, 64);
@@ -362,6 +367,7 @@ void prod_n_tc(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t ldI, int64_t J, const d
   p.n_tiles = p.n_gene_tiles * nchunk;
   if (ws.part.n < (int64_t)nchunk * bp * ldI) ws.part.alloc((int64_t)nchunk * bp * ldI);
   p.out = ws.part.get(); p.ldo = ldI;
+  p.use_lo = use_lo ? 1 : 0;
   p.a_lbo = (uint32_t)env_int("SCGBM_TC_LBO", 8192);
   p.a_sbo = (uint32_t)env_int("SCGBM_TC_SBO", 1024);
   const CUtensorMap mh = make_tmap_2d(R.hi, 2, false, (uint64_t)ldI, (uint64_t)J, (uint64_t)ldI * 2, 64, 64);
@@ -386,7 +392,7 @@ void prod_t_tc(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t ldI, int64_t J, const d
   p.n_gene_tiles = 1;
   p.n_tiles = (int)ceil_div(J, 128);
   p.kb_t = (int)(ldI / TC_KB);
-  p.c = c; p.out = out; p.ldo = ldo; p.op_inv_scale = ws.opmeta.get() + 1;
+  p.c = c; p.out = out; p.ldo = ldo; p.op_inv_scale = ws.opmeta.get() + 1; p.use_lo = 1;
   const CUtensorMap mh = make_tmap_2d(R.hi, 2, false, (uint64_t)ldI, (uint64_t)J, (uint64_t)ldI * 2, 64, 64);
   const CUtensorMap ml = make_tmap_2d(R.lo, 2, false, (uint64_t)ldI, (uint64_t)J, (uint64_t)ldI * 2, 64, 64);
   const CUtensorMap mb = make_tmap_2d(ws.op16.get(), 2, false, (uint64_t)ldI, (uint64_t)(2 * bp), (uint64_t)ldI * 2, 64, 2 * bp);

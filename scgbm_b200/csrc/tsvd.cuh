@@ -36,6 +36,7 @@ struct TsvdOpts {
   int max_cycles = 40;  // restarts (cold start on gap-less spectra)
   uint64_t seed = 0;
   int variant = PROD_AUTO;
+  int fast = 0;         // allow 2-pass calls (no Krylov extension) while the previous estimate is < tol^2
 };
 
 struct TsvdWs {
@@ -49,6 +50,8 @@ struct TsvdWs {
   bool warm = false;
   int b = 0;
   int64_t passes_total = 0, calls = 0;
+  double last_est = 1e300;  // residual estimate of the last call that ran a Krylov extension
+  int fast_streak = 0;      // consecutive calls that skipped the extension
 };
 
 // outU: ldI x M, outD: M, outV: ldJ x M (device, column-major)
