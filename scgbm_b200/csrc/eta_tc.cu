@@ -365,7 +365,8 @@ ll_const_kernel(int64_t I, const double* __restrict__ alpha, const double* __res
 // ---------------------------------------------------------------------------------
 // K3 row sums:  S_i = sum_j g_j exp(x_ij);   D[128 genes x 128 cells], thread = gene
 // ---------------------------------------------------------------------------------
-constexpr int RT_NT = 320;
+constexpr int RT_NT = 576;            // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue (SFU-bound: keep the XU pipe fed)
+constexpr int RT_EPI = 512;
 constexpr int RT_TILE = 128;
 constexpr int RT_SLAB = RT_TILE * 128;
 
@@ -373,9 +374,9 @@ struct RowsumTcParams {
   int64_t J, ldI;
   int nslab, kk;
   int n_gene_tiles, n_chunks, cell_tiles_per_chunk, n_cell_tiles;
-  const float* g_col;
+  const float* g_col;   // exp(beta_j), zero padded to a multiple of 128 cells
   const float* inv_a; const float* inv_b;
-  double* row_part;     // [chunk][ldI]
+  double* row_part;     // [chunk][4][ldI]
 };
 
 template <bool CLAMP>
@@ -391,7 +392,6 @@ rowsum_tc_kernel(const __grid_constant__ CUtensorMap map_genes, const __grid_con
   uint64_t* b_full = bars + 2;    uint64_t* b_empty = bars + 4;
   uint64_t* d_full = bars + 6;    uint64_t* d_empty = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-  float* g_s = reinterpret_cast<float*>(bars + 12);        // [2][128] g_j of the cell tile in flight
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -399,7 +399,7 @@ rowsum_tc_kernel(const __grid_constant__ CUtensorMap map_genes, const __grid_con
     tc::mbar_init(a_full, 1); tc::mbar_init(a_empty, 1);
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1);
-      tc::mbar_init(&d_full[s], 1); tc::mbar_init(&d_empty[s], 256);
+      tc::mbar_init(&d_full[s], 1); tc::mbar_init(&d_empty[s], RT_EPI);
     }
     tc::fence_barrier_init();
   }
@@ -466,9 +466,8 @@ rowsum_tc_kernel(const __grid_constant__ CUtensorMap map_genes, const __grid_con
       }
     }
   } else {
-    const int e = warp - 2, q = warp & 3, ch = e >> 2;   // ch: cells ch*64 .. +63 of the tile
+    const int e = warp - 2, q = warp & 3, ch = e >> 2;   // ch: cells ch*32 .. +31 of the tile
     const int row = q * 32 + lane;                       // tile-local gene
-    const int et = threadIdx.x - 64;
     const float inv = __ldg(p.inv_a) * __ldg(p.inv_b);
     const float L_hi = 1.4426950216293335f * inv, L_lo = 1.9259629911e-08f * inv;
     const float clampv = 8.0f / inv;
@@ -479,25 +478,20 @@ rowsum_tc_kernel(const __grid_constant__ CUtensorMap map_genes, const __grid_con
       unit_info(unit, gt, ct0, nct);
       double s64 = 0.0;
       for (int c = 0; c < nct; ++c) {
-        // stage g_j of this cell tile (double buffered with the TMEM accumulator)
-        if (et < RT_TILE) {
-          const int64_t cell = (int64_t)(ct0 + c) * RT_TILE + et;
-          g_s[db * RT_TILE + et] = cell < p.J ? __ldg(p.g_col + cell) : 0.0f;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float* gp = p.g_col + (int64_t)(ct0 + c) * RT_TILE + ch * 32;
         tc::mbar_wait(&d_full[db], dph[db]);
         dph[db] ^= 1;
         tc::fence_after_sync();
         float ts = 0.0f;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int col = ch * 64 + cc * 16;
+        for (int cc = 0; cc < 2; ++cc) {
+          const int col = ch * 32 + cc * 16;
           uint32_t xr[16];
           tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + db * RT_TILE + col, xr);
           float gj[16];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float4 g4 = *reinterpret_cast<const float4*>(g_s + db * RT_TILE + col + 4 * k);
+          for (int k = 0; k < 4; ++k) {     // same address in every lane: one broadcast transaction
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(gp + cc * 16) + k);
             gj[4 * k] = g4.x; gj[4 * k + 1] = g4.y; gj[4 * k + 2] = g4.z; gj[4 * k + 3] = g4.w;
           }
           tc::tmem_wait_ld();
@@ -513,10 +507,10 @@ rowsum_tc_kernel(const __grid_constant__ CUtensorMap map_genes, const __grid_con
         tc::mbar_arrive(&d_empty[db]);
         db ^= 1;
       }
-      // the two column halves of a gene meet in the fixed-order second stage: [chunk][half][ldI]
+      // the four column quarters of a gene meet in the fixed-order second stage: [chunk][quarter][ldI]
       const int chunk = unit / p.n_gene_tiles;
       const int64_t gene = (int64_t)gt * RT_TILE + row;
-      if (gene < p.ldI) p.row_part[((int64_t)chunk * 2 + ch) * p.ldI + gene] = s64;
+      if (gene < p.ldI) p.row_part[((int64_t)chunk * 4 + ch) * p.ldI + gene] = s64;
     }
   }
   tc::fence_before_sync();
@@ -603,9 +597,9 @@ void pass_rowsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, cons
   p.g_col = g_col;
   p.inv_a = fa.meta.get() + 1; p.inv_b = fb.meta.get() + 1;
   const int64_t n = g.ldI;
-  if (ws.row_part.n < (int64_t)p.n_chunks * 2 * n) ws.row_part.alloc((int64_t)p.n_chunks * 2 * n);
+  if (ws.row_part.n < (int64_t)p.n_chunks * 4 * n) ws.row_part.alloc((int64_t)p.n_chunks * 4 * n);
   p.row_part = ws.row_part.get();
-  const int smem_bytes = 3 * p.nslab * RT_SLAB + 1024 + 128 + 2 * RT_TILE * 4;
+  const int smem_bytes = 3 * p.nslab * RT_SLAB + 1024 + 128;
   const int n_units = p.n_gene_tiles * p.n_chunks;
   const int grid = std::min(n_units, ctx.num_sms);
   const CUtensorMap mg = make_tmap_2d(fa.data.get(), 2, false, (uint64_t)fa.Kp, (uint64_t)fa.rows_pad, (uint64_t)fa.Kp * 2, 64, RT_TILE, 128);
@@ -621,7 +615,7 @@ void pass_rowsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, cons
     }
     SCGBM_LAUNCH_CHECK();
   }
-  rowpart_reduce_launch(ctx, p.n_chunks * 2, n, ws.row_part.get(), S);
+  rowpart_reduce_launch(ctx, p.n_chunks * 4, n, ws.row_part.get(), S);
 }
 
 }  // namespace scgbm

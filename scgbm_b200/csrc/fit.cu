@@ -280,7 +280,8 @@ struct FitState {
     beta.alloc(ldJ); beta0.alloc(ldJ); logcs.alloc(ldJ); Ccol.alloc(ldJ);
     logtot.alloc(nbatch); shift.alloc(1);
     f_row.alloc(ldI * nbatch); la_row.alloc(ldI * nbatch); s_row.alloc(ldI * nbatch);
-    g_col.alloc(ldJ); lb_col.alloc(ldJ); t_col.alloc(ldJ);
+    g_col.alloc(ldJ + 128); lb_col.alloc(ldJ); t_col.alloc(ldJ);   // g_col: zero tail for whole 128-cell tiles
+    g_col.zero(ctx.stream);
     alpha.zero(ctx.stream); beta.zero(ctx.stream); logcs.zero(ctx.stream);
     for (auto& f : slot) f.alloc(ldI, ldJ, M);
 
@@ -714,7 +715,8 @@ void dbg_eval_impl(const scgbm_eval_args* a, scgbm_eval_out* out) {
   DevBuf<double> Xu(std::max<int64_t>(ldI * Mx, 1)), Xv(std::max<int64_t>(ldJ * Mx, 1)), alpha(ldI), beta(ldJ),
       logrs(ldI), logcs(ldJ), S(ldI), Cc(ldJ), shift(1), scal(4), tmp(std::max(ldI, ldJ));
   DevBuf<float> A32(std::max<int64_t>(ldI * Mx, 1)), B32(std::max<int64_t>(ldJ * Mx, 1)), f_row(ldI), la_row(ldI),
-      g_col(ldJ), lb_col(ldJ), rs32(ldI), cs32(ldJ);
+      g_col(ldJ + 128), lb_col(ldJ), rs32(ldI), cs32(ldJ);
+  g_col.zero(ctx.stream);
   DevBuf<uint16_t> Rhi(ldI * J), Rlo(ldI * J);
   ResidBuf R; R.hi = Rhi.get(); R.lo = Rlo.get(); R.scale = resid_scale_for(Y.maxY);
   alpha.zero(ctx.stream); beta.zero(ctx.stream);
