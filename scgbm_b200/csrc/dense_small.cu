@@ -70,15 +70,20 @@ ts_gram_partial(int64_t n, int p, int q, const double* __restrict__ A, int64_t l
     }
 }
 
+// one warp per output entry: lanes stride over the chunks, fixed-order shuffle tree
 __global__ void ts_gram_reduce(int nchunk, int p, int q, const double* __restrict__ part,
                                double* __restrict__ C, int ldc, double alpha, double beta) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
   if (idx >= p * q) return;
   double s = 0.0;
-  for (int c = 0; c < nchunk; ++c) s += part[(int64_t)c * p * q + idx];
-  const int pi = idx % p, qi = idx / p;
-  double* dst = &C[(int64_t)qi * ldc + pi];
-  *dst = (beta == 0.0 ? 0.0 : beta * (*dst)) + alpha * s;
+  for (int c = lane; c < nchunk; c += 32) s += part[(int64_t)c * p * q + idx];
+  s = warp_sum(s);
+  if (lane == 0) {
+    const int pi = idx % p, qi = idx / p;
+    double* dst = &C[(int64_t)qi * ldc + pi];
+    *dst = (beta == 0.0 ? 0.0 : beta * (*dst)) + alpha * s;
+  }
 }
 
 void ts_gram(Ctx& ctx, SmallWs& ws, int64_t n, int p, int q, const double* A, int64_t lda,
@@ -95,7 +100,7 @@ void ts_gram(Ctx& ctx, SmallWs& ws, int64_t n, int p, int q, const double* A, in
   ts_gram_partial<<<grid, GR_NT, 0, ctx.stream>>>(n, p, q, A, lda, B, ldb, ws.partial.get(),
                                                   rows_per_chunk);
   SCGBM_LAUNCH_CHECK();
-  ts_gram_reduce<<<(unsigned)ceil_div(p * q, 256), 256, 0, ctx.stream>>>(nchunk, p, q, ws.partial.get(),
+  ts_gram_reduce<<<(unsigned)ceil_div((int64_t)p * q * 32, 256), 256, 0, ctx.stream>>>(nchunk, p, q, ws.partial.get(),
                                                                         C, ldc, alpha, beta);
   SCGBM_LAUNCH_CHECK();
 }
