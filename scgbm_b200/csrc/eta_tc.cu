@@ -153,18 +153,18 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
       for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
         int ct, gt0, ngt;
         unit_info(unit, ct, gt0, ngt);
-        tc::mbar_wait(a_empty, aph ^ 1);
+        tc::mbar_wait_relaxed(a_empty, aph ^ 1);
         tc::mbar_arrive_expect_tx(a_full, p.nslab * FT_SLAB_A);
         for (int s = 0; s < p.nslab; ++s) tc::tma_load_2d(&map_cells, a_full, a_buf + s * FT_SLAB_A, s * 64, ct * FT_CELLS);
         aph ^= 1;
         for (int g = 0; g < ngt; ++g) {
           const int gene0 = (gt0 + g) * FT_GENES;
-          tc::mbar_wait(&b_empty[bs], bph ^ 1);
+          tc::mbar_wait_relaxed(&b_empty[bs], bph ^ 1);
           tc::mbar_arrive_expect_tx(&b_full[bs], p.nslab * FT_SLAB_B);
           for (int s = 0; s < p.nslab; ++s)
             tc::tma_load_2d(&map_genes, &b_full[bs], b_buf + (bs * p.nslab + s) * FT_SLAB_B, s * 64, gene0);
           if (++bs == 2) { bs = 0; bph ^= 1; }
-          tc::mbar_wait(&y_empty[ys], yph ^ 1);
+          tc::mbar_wait_relaxed(&y_empty[ys], yph ^ 1);
           tc::mbar_arrive_expect_tx(&y_full[ys], p.y_stage_bytes);
           tc::tma_load_2d(&map_y, &y_full[ys], y_buf + ys * p.y_stage_bytes, gene0, ct * FT_CELLS);
           if (++ys == (uint32_t)p.y_stages) { ys = 0; yph ^= 1; }
@@ -423,12 +423,12 @@ rowsum_tc_kernel(const __grid_constant__ CUtensorMap map_genes, const __grid_con
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         int gt, ct0, nct;
         unit_info(unit, gt, ct0, nct);
-        tc::mbar_wait(a_empty, aph ^ 1);
+        tc::mbar_wait_relaxed(a_empty, aph ^ 1);
         tc::mbar_arrive_expect_tx(a_full, p.nslab * RT_SLAB);
         for (int s = 0; s < p.nslab; ++s) tc::tma_load_2d(&map_genes, a_full, a_buf + s * RT_SLAB, s * 64, gt * RT_TILE);
         aph ^= 1;
         for (int c = 0; c < nct; ++c) {
-          tc::mbar_wait(&b_empty[bs], bph ^ 1);
+          tc::mbar_wait_relaxed(&b_empty[bs], bph ^ 1);
           tc::mbar_arrive_expect_tx(&b_full[bs], p.nslab * RT_SLAB);
           for (int s = 0; s < p.nslab; ++s)
             tc::tma_load_2d(&map_cells, &b_full[bs], b_buf + (bs * p.nslab + s) * RT_SLAB, s * 64, (ct0 + c) * RT_TILE);
