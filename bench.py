@@ -222,6 +222,9 @@ def main():
     comm = None
     dist = None
     if world > 1:
+        # stdout must carry exactly one JSON line: NCCL_DEBUG=VERSION would print a banner there
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist
         dist.init_process_group("gloo", rank=rank, world_size=world)
