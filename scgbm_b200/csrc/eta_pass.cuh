@@ -61,6 +61,8 @@ bool eta_tc_supported(const PassGeom& g, const XDesc& x, int y_storage /* -1: pa
 void stage_factor16(Ctx& ctx, Factor16& f, int64_t n_real, int64_t ld, int M, int side, const double* U,
                     const double* d, const float* rs);
 void pass_rowsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* g_col, double* S);
+// f_row / g_col must be zero padded by 128 entries beyond ldI / ldJ (whole 128-wide tiles are read)
+void pass_colsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* f_row, double* C);
 // alpha/beta (fp64) and this rank's row sums of Y close the objective:
 //   sum_nz Y log W = sum Y x + sum_i alpha_i rs_i + sum_j beta_j cs_j   (+ clip correction)
 void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const Counts& y, const float* f_row,

@@ -17,6 +17,7 @@
 //     sum_nz Y log W = sum Y*x + sum_i alpha_i rs_i + sum_j beta_j cs_j (+ clip correction).
 //   rowsum_tc_kernel (K3, R/fit.R:127-130): D[128 genes x 128 cells]; epilogue thread = one
 //     gene, accumulates g_j exp(x_ij) over the cells; touches no I x J memory (SFU-bound).
+//     With the factors swapped the same kernel gives the column sums of R/fit.R:133-135.
 #include "eta_pass.cuh"
 #include "tc_common.cuh"
 
@@ -582,40 +583,51 @@ void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const
   }
 }
 
-void pass_rowsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* g_col, double* S) {
-  const Factor16& fa = *x.A16;
-  const Factor16& fb = *x.B16;
+// out[r] = sum_c colfac[c] * exp(x_rc) for the rows of `lanes` (TMEM lanes) against all rows of
+// `streamed` (TMEM columns).  rowsum: lanes = genes, streamed = cells, colfac = exp(beta);
+// colsum: lanes = cells, streamed = genes, colfac = exp(alpha).  colfac is zero padded to whole tiles.
+static void lane_sums_tc(Ctx& ctx, EtaWs& ws, const Factor16& lanes, const Factor16& streamed, int64_t ld_lanes,
+                         int64_t n_streamed, const float* colfac, bool clamp, double* out, int prof_class) {
   RowsumTcParams p;
   memset(&p, 0, sizeof(p));
-  p.J = g.J; p.ldI = g.ldI;
-  p.nslab = fa.Kp / 64; p.kk = 3 * fa.Mp / 16;
-  p.n_gene_tiles = (int)ceil_div(g.ldI, RT_TILE);
-  p.n_cell_tiles = (int)ceil_div(g.J, RT_TILE);
+  p.J = n_streamed; p.ldI = ld_lanes;
+  p.nslab = lanes.Kp / 64; p.kk = 3 * lanes.Mp / 16;
+  p.n_gene_tiles = (int)ceil_div(ld_lanes, RT_TILE);
+  p.n_cell_tiles = (int)ceil_div(n_streamed, RT_TILE);
   int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div((int64_t)ctx.num_sms * 8, p.n_gene_tiles), ceil_div(p.n_cell_tiles, 4)));
   p.cell_tiles_per_chunk = (int)ceil_div(p.n_cell_tiles, chunks);
   p.n_chunks = (int)ceil_div(p.n_cell_tiles, p.cell_tiles_per_chunk);
-  p.g_col = g_col;
-  p.inv_a = fa.meta.get() + 1; p.inv_b = fb.meta.get() + 1;
-  const int64_t n = g.ldI;
+  p.g_col = colfac;
+  p.inv_a = lanes.meta.get() + 1; p.inv_b = streamed.meta.get() + 1;
+  const int64_t n = ld_lanes;
   if (ws.row_part.n < (int64_t)p.n_chunks * 4 * n) ws.row_part.alloc((int64_t)p.n_chunks * 4 * n);
   p.row_part = ws.row_part.get();
   const int smem_bytes = 3 * p.nslab * RT_SLAB + 1024 + 128;
   const int n_units = p.n_gene_tiles * p.n_chunks;
   const int grid = std::min(n_units, ctx.num_sms);
-  const CUtensorMap mg = make_tmap_2d(fa.data.get(), 2, false, (uint64_t)fa.Kp, (uint64_t)fa.rows_pad, (uint64_t)fa.Kp * 2, 64, RT_TILE, 128);
-  const CUtensorMap mc = make_tmap_2d(fb.data.get(), 2, false, (uint64_t)fb.Kp, (uint64_t)fb.rows_pad, (uint64_t)fb.Kp * 2, 64, RT_TILE, 128);
+  const CUtensorMap ml = make_tmap_2d(lanes.data.get(), 2, false, (uint64_t)lanes.Kp, (uint64_t)lanes.rows_pad, (uint64_t)lanes.Kp * 2, 64, RT_TILE, 128);
+  const CUtensorMap ms = make_tmap_2d(streamed.data.get(), 2, false, (uint64_t)streamed.Kp, (uint64_t)streamed.rows_pad, (uint64_t)streamed.Kp * 2, 64, RT_TILE, 128);
   {
-    ProfScope ps(ctx.prof, SCGBM_K_ROWSUM, 1);
-    if (x.clamp) {
+    ProfScope ps(ctx.prof, prof_class, 1);
+    if (clamp) {
       SCGBM_CUDA(cudaFuncSetAttribute(rowsum_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-      rowsum_tc_kernel<true><<<grid, RT_NT, smem_bytes, ctx.stream>>>(mg, mc, p);
+      rowsum_tc_kernel<true><<<grid, RT_NT, smem_bytes, ctx.stream>>>(ml, ms, p);
     } else {
       SCGBM_CUDA(cudaFuncSetAttribute(rowsum_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-      rowsum_tc_kernel<false><<<grid, RT_NT, smem_bytes, ctx.stream>>>(mg, mc, p);
+      rowsum_tc_kernel<false><<<grid, RT_NT, smem_bytes, ctx.stream>>>(ml, ms, p);
     }
     SCGBM_LAUNCH_CHECK();
   }
-  rowpart_reduce_launch(ctx, p.n_chunks * 4, n, ws.row_part.get(), S);
+  rowpart_reduce_launch(ctx, p.n_chunks * 4, n, ws.row_part.get(), out);
+}
+
+void pass_rowsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* g_col, double* S) {
+  lane_sums_tc(ctx, ws, *x.A16, *x.B16, g.ldI, g.J, g_col, x.clamp != 0, S, SCGBM_K_ROWSUM);
+}
+
+// C_j = sum_i f_i exp(x_ij)   (R/fit.R:134): the same kernel with the roles of the factors swapped
+void pass_colsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* f_row, double* C) {
+  lane_sums_tc(ctx, ws, *x.B16, *x.A16, g.ldJ, g.ldI, f_row, x.clamp != 0, C, SCGBM_K_COLSUM);
 }
 
 }  // namespace scgbm

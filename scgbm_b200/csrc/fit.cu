@@ -279,7 +279,8 @@ struct FitState {
     alpha.alloc(ldI * nbatch); alpha0.alloc(ldI * nbatch); logrs.alloc(ldI * nbatch); S.alloc(ldI * nbatch);
     beta.alloc(ldJ); beta0.alloc(ldJ); logcs.alloc(ldJ); Ccol.alloc(ldJ);
     logtot.alloc(nbatch); shift.alloc(1);
-    f_row.alloc(ldI * nbatch); la_row.alloc(ldI * nbatch); s_row.alloc(ldI * nbatch);
+    f_row.alloc(ldI * nbatch + 128); la_row.alloc(ldI * nbatch); s_row.alloc(ldI * nbatch);   // f_row: zero tail (tiles)
+    f_row.zero(ctx.stream);
     g_col.alloc(ldJ + 128); lb_col.alloc(ldJ); t_col.alloc(ldJ);   // g_col: zero tail for whole 128-cell tiles
     g_col.zero(ctx.stream);
     alpha.zero(ctx.stream); beta.zero(ctx.stream); logcs.zero(ctx.stream);
@@ -459,7 +460,8 @@ struct FitRun {
     }
     st.stage_rows();
     if (a.infer_beta) {                                  // R/fit.R:133-135
-      pass_colsum(ctx, st.eta, st.geom, xc, st.f_row.get(), st.Ccol.get());
+      if (tc_eta) pass_colsum_tc(ctx, st.eta, st.geom, xc, st.f_row.get(), st.Ccol.get());
+      else pass_colsum(ctx, st.eta, st.geom, xc, st.f_row.get(), st.Ccol.get());
       ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
       beta_infer_kernel<<<GRID1(J)>>>(J, st.logcs.get(), st.Ccol.get(), st.beta.get());
       SCGBM_LAUNCH_CHECK();
@@ -714,9 +716,9 @@ void dbg_eval_impl(const scgbm_eval_args* a, scgbm_eval_out* out) {
   PassGeom geom{I, J, ldI, ldJ, 1, nullptr};
   DevBuf<double> Xu(std::max<int64_t>(ldI * Mx, 1)), Xv(std::max<int64_t>(ldJ * Mx, 1)), alpha(ldI), beta(ldJ),
       logrs(ldI), logcs(ldJ), S(ldI), Cc(ldJ), shift(1), scal(4), tmp(std::max(ldI, ldJ));
-  DevBuf<float> A32(std::max<int64_t>(ldI * Mx, 1)), B32(std::max<int64_t>(ldJ * Mx, 1)), f_row(ldI), la_row(ldI),
+  DevBuf<float> A32(std::max<int64_t>(ldI * Mx, 1)), B32(std::max<int64_t>(ldJ * Mx, 1)), f_row(ldI + 128), la_row(ldI),
       g_col(ldJ + 128), lb_col(ldJ), rs32(ldI), cs32(ldJ);
-  g_col.zero(ctx.stream);
+  g_col.zero(ctx.stream); f_row.zero(ctx.stream);
   DevBuf<uint16_t> Rhi(ldI * J), Rlo(ldI * J);
   ResidBuf R; R.hi = Rhi.get(); R.lo = Rlo.get(); R.scale = resid_scale_for(Y.maxY);
   alpha.zero(ctx.stream); beta.zero(ctx.stream);
@@ -758,7 +760,8 @@ void dbg_eval_impl(const scgbm_eval_args* a, scgbm_eval_out* out) {
   beta_shift_kernel<<<GRID1(J)>>>(J, beta.get(), shift.get());
   exp_stage_kernel<<<GRID1(ldI)>>>(I, ldI, 1, alpha.get(), 1.0, f_row.get(), la_row.get());
   if (a->infer_beta) {
-    pass_colsum(ctx, eta, geom, x, f_row.get(), Cc.get());
+    if (tc_eta) pass_colsum_tc(ctx, eta, geom, x, f_row.get(), Cc.get());
+    else pass_colsum(ctx, eta, geom, x, f_row.get(), Cc.get());
     beta_infer_kernel<<<GRID1(J)>>>(J, logcs.get(), Cc.get(), beta.get());
   }
   exp_stage_kernel<<<GRID1(ldJ)>>>(J, ldJ, 1, beta.get(), 1.0, g_col.get(), lb_col.get());
