@@ -65,6 +65,8 @@ CASES = [
     (400, 300, 4, 6, dict(max_iter=12), dict()),                        # hits max.iter
     (333, 777, 6, 6, dict(tol=1e-10, infer_beta=True, max_iter=60), dict(amean=-1.0)),   # figures/scGBM_sim.R:85
     (512, 640, 5, 20, dict(min_iter=10, max_iter=40), dict(nb=2.0)),    # M = 20
+    (400, 520, 6, 50, dict(max_iter=8), dict()),                        # M = 50 (config 5): 64-wide Krylov block, 3 K slabs
+    (40, 33, 2, 2, dict(max_iter=15), dict()),                          # smaller than one tile in both directions
 ]
 
 
