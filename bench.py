@@ -335,6 +335,7 @@ def main():
                "d2h_bytes_per_step": prof["d2h_bytes"] / n_it, "fit_seconds": wall, "iterations": n_it,
                "accepted": int(len(out["obj"])), "device_ms": prof["total_ms"], "host_dtype": "int32",
                "pinned": bool(pinned), "objective_first_last": [float(out["obj"][0]), float(out["obj"][-1])],
+               "kernel_ms": {k: round(v, 1) for k, v in prof["ms"].items()},
                "call": f"gbm_sc(Y, M={M}, max_iter={args.e2e_max_iter}, return_W=False) with reference defaults tol=1e-4, min_iter=30"}
         del Yh
         if pinned:

@@ -210,8 +210,15 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
     const int row = q * 32 + lane;          // tile-local cell
     const int et = threadIdx.x - 64;        // 0..255
     const float inv = __ldg(p.inv_a) * __ldg(p.inv_b);
-    const float L_hi = 1.4426950216293335f * inv, L_lo = 1.9259629911e-08f * inv;   // log2(e) / (sA sB), split
+    const float L2E = 1.4426950408889634f * inv;   // log2(e) / (sA sB): one rounding of the product, <= 2^-24 |t|
     const float clampv = 8.0f / inv;
+    // everything W-sized is carried pre-multiplied by the residual scale 2^k (exact): the count
+    // comes out of the magic-number conversion already scaled, g_j and max.Y are scaled once
+    const int kexp = (int)((__float_as_uint(p.rscale) >> 23) & 0xffu) - 127;
+    const uint32_t magic_bits = (uint32_t)(150 + kexp) << 23;       // 2^(23+k)
+    const float magic = __uint_as_float(magic_bits);
+    const float maxYs = p.maxY * p.rscale;
+    const float inv_rs = 1.0f / p.rscale;
     double sw64 = 0.0, syl64 = 0.0;
     float mw = 0.0f;
     uint32_t ys = 0, yph = 0, db = 0, rb = 0;
@@ -221,7 +228,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
       unit_info(unit, ct, gt0, ngt);
       const int64_t cell = (int64_t)ct * FT_CELLS + row;
       const bool cell_ok = cell < p.J;
-      const float gj = cell_ok ? __ldg(p.g_col + cell) : 0.0f;
+      const float gj = cell_ok ? __ldg(p.g_col + cell) * p.rscale : 0.0f;
       const float lbj = cell_ok ? __ldg(p.lb_col + cell) : 0.0f;
       for (int g = 0; g < ngt; ++g) {
         const int gene0 = (gt0 + g) * FT_GENES;
@@ -247,16 +254,18 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
             const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
             for (int k = 0; k < 8; ++k) {   // exact small-int -> float on the ALU/FMA pipes (the XU pipe is busy with ex2)
-              y[2 * k] = __uint_as_float(0x4B000000u | (w[k] & 0xffffu)) - 8388608.0f;
-              y[2 * k + 1] = __uint_as_float(0x4B000000u | (w[k] >> 16)) - 8388608.0f;
+              y[2 * k] = __uint_as_float(magic_bits | (w[k] & 0xffffu)) - magic;        // = 2^k * count, exact
+              y[2 * k + 1] = __uint_as_float(magic_bits | (w[k] >> 16)) - magic;
             }
           } else {
             const uint4 v0 = *reinterpret_cast<const uint4*>(yt + row * 64 + col);
             const uint32_t w[4] = {v0.x, v0.y, v0.z, v0.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              y[4 * k] = (float)(w[k] & 0xffu); y[4 * k + 1] = (float)((w[k] >> 8) & 0xffu);
-              y[4 * k + 2] = (float)((w[k] >> 16) & 0xffu); y[4 * k + 3] = (float)(w[k] >> 24);
+              y[4 * k] = __uint_as_float(magic_bits | (w[k] & 0xffu)) - magic;
+              y[4 * k + 1] = __uint_as_float(magic_bits | ((w[k] >> 8) & 0xffu)) - magic;
+              y[4 * k + 2] = __uint_as_float(magic_bits | ((w[k] >> 16) & 0xffu)) - magic;
+              y[4 * k + 3] = __uint_as_float(magic_bits | (w[k] >> 24)) - magic;
             }
           }
           float f[16];
@@ -273,27 +282,26 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
             float xs = __uint_as_float(xr[k]);                        // sA sB x
             if (CLAMP) xs = fminf(fmaxf(xs, -clampv), clampv);        // R/fit.R:119-120
             xr[k] = __float_as_uint(xs);
-            const float t = fmaf(xs, L_lo, xs * L_hi);
-            const float w = ex2_approx(t) * (f[k] * gj);
+            const float w = ex2_approx(xs * L2E) * (f[k] * gj);       // 2^k W
             wv[k] = w;
             cm = fmaxf(cm, w);
-            const float wc = fminf(w, p.maxY);                        // R/fit.R:145
+            const float wc = fminf(w, maxYs);                         // R/fit.R:145
             tsw += wc;
             tsyl = fmaf(y[k], xs, tsyl);                              // sum Y x (scaled)
-            r[k] = (y[k] - wc) * p.rscale;
+            r[k] = y[k] - wc;                                         // 2^k (Y - W)
           }
           double corr = 0.0;
-          if (cm > p.maxY) {   // rare: clipped entries take log(max.Y) instead of eta in the objective
+          if (cm > maxYs) {   // rare: clipped entries take log(max.Y) instead of eta in the objective
 #pragma unroll
             for (int k = 0; k < 16; ++k)
-              if (wv[k] > p.maxY && y[k] != 0.0f) {
+              if (wv[k] > maxYs && y[k] != 0.0f) {
                 const float lw = __uint_as_float(xr[k]) * inv + (__ldg(p.la_row + gene0 + col + k) + lbj);
-                corr += (double)y[k] * (double)(p.log_maxY - lw);
+                corr += (double)(y[k] * inv_rs) * (double)(p.log_maxY - lw);
               }
           }
           sw64 += (double)tsw;
-          syl64 += (double)tsyl * (double)inv + corr;
-          mw = fmaxf(mw, fminf(cm, p.maxY));
+          syl64 += (double)tsyl * (double)(inv * inv_rs) + corr;
+          mw = fmaxf(mw, fminf(cm, maxYs));
           // fp16 planes, 16 genes = 32 bytes per plane: two 16-byte swizzled chunks
           uint32_t hp[8], lp[8];
 #pragma unroll
@@ -330,7 +338,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
     }
     if (et == 0) tc::tma_store_wait<0>();
     // CTA partial of the three scalars (fixed order)
-    sw64 = warp_sum(sw64); syl64 = warp_sum(syl64); mw = warp_max(mw);
+    sw64 = warp_sum(sw64) * (double)inv_rs; syl64 = warp_sum(syl64); mw = warp_max(mw) * inv_rs;
     if (lane == 0) { red[e * 4 + 0] = sw64; red[e * 4 + 1] = syl64; red[e * 4 + 2] = (double)mw; }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (et == 0) {
