@@ -241,25 +241,43 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const uint8_t* yt = y_buf + ys * p.y_stage_bytes;
         uint8_t* rt = r_buf + rb * FT_R_BYTES;
+        // issue every load of the tile's two chunks first (TMEM, Y from smem, f_i broadcast), wait once,
+        // hand the TMEM buffer back to the MMA warp, then do the arithmetic
+        uint32_t xr2[2][16];
+        uint4 yv[2][2];
+        float4 fv[2][4];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const int col = ch * 32 + c * 16;            // first gene of the chunk within the tile
-          uint32_t xr[16];
-          tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + db * FT_GENES + col, xr);
-          float y[16];
+          tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + db * FT_GENES + col, xr2[c]);
           if (sizeof(YT) == 2) {
             const int q0 = col >> 3;                   // 16-byte chunk index (8 genes each)
-            const uint4 v0 = *reinterpret_cast<const uint4*>(yt + row * 128 + (((q0) ^ (row & 7)) << 4));
-            const uint4 v1 = *reinterpret_cast<const uint4*>(yt + row * 128 + (((q0 + 1) ^ (row & 7)) << 4));
-            const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            yv[c][0] = *reinterpret_cast<const uint4*>(yt + row * 128 + (((q0) ^ (row & 7)) << 4));
+            yv[c][1] = *reinterpret_cast<const uint4*>(yt + row * 128 + (((q0 + 1) ^ (row & 7)) << 4));
+          } else {
+            yv[c][0] = *reinterpret_cast<const uint4*>(yt + row * 64 + col);
+            yv[c][1] = make_uint4(0u, 0u, 0u, 0u);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) fv[c][k] = __ldg(reinterpret_cast<const float4*>(p.f_row + gene0 + col) + k);
+        }
+        tc::tmem_wait_ld();
+        tc::fence_before_sync();
+        tc::mbar_arrive(&d_empty[db]);                 // accumulator is in registers: the next MMA may overwrite it
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col = ch * 32 + c * 16;
+          uint32_t (&xr)[16] = xr2[c];
+          float y[16];
+          if (sizeof(YT) == 2) {
+            const uint32_t w[8] = {yv[c][0].x, yv[c][0].y, yv[c][0].z, yv[c][0].w, yv[c][1].x, yv[c][1].y, yv[c][1].z, yv[c][1].w};
 #pragma unroll
             for (int k = 0; k < 8; ++k) {   // exact small-int -> float on the ALU/FMA pipes (the XU pipe is busy with ex2)
               y[2 * k] = __uint_as_float(magic_bits | (w[k] & 0xffffu)) - magic;        // = 2^k * count, exact
               y[2 * k + 1] = __uint_as_float(magic_bits | (w[k] >> 16)) - magic;
             }
           } else {
-            const uint4 v0 = *reinterpret_cast<const uint4*>(yt + row * 64 + col);
-            const uint32_t w[4] = {v0.x, v0.y, v0.z, v0.w};
+            const uint32_t w[4] = {yv[c][0].x, yv[c][0].y, yv[c][0].z, yv[c][0].w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               y[4 * k] = __uint_as_float(magic_bits | (w[k] & 0xffu)) - magic;
@@ -270,11 +288,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
           }
           float f[16];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float4 f4 = __ldg(reinterpret_cast<const float4*>(p.f_row + gene0 + col) + k);
-            f[4 * k] = f4.x; f[4 * k + 1] = f4.y; f[4 * k + 2] = f4.z; f[4 * k + 3] = f4.w;
-          }
-          tc::tmem_wait_ld();
+          for (int k = 0; k < 4; ++k) { f[4 * k] = fv[c][k].x; f[4 * k + 1] = fv[c][k].y; f[4 * k + 2] = fv[c][k].z; f[4 * k + 3] = fv[c][k].w; }
           float tsw = 0.0f, tsyl = 0.0f, cm = 0.0f;
           float wv[16], r[16];
 #pragma unroll
@@ -320,9 +334,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
           *reinterpret_cast<uint4*>(rl + (((q0) ^ (row & 7)) << 4)) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
           *reinterpret_cast<uint4*>(rl + (((q0 + 1) ^ (row & 7)) << 4)) = make_uint4(lp[4], lp[5], lp[6], lp[7]);
         }
-        // TMEM buffer and Y stage are free again
-        tc::fence_before_sync();
-        tc::mbar_arrive(&d_empty[db]);
+        // the Y stage is free again
         tc::mbar_arrive(&y_empty[ys]);
         // hand the tile to the TMA store
         tc::fence_proxy_async();
