@@ -233,10 +233,10 @@ prod_t_kernel(const uint16_t* __restrict__ Rhi, const uint16_t* __restrict__ Rlo
 }
 
 void prod_t(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t I, int64_t ldI, int64_t J, const double* Q,
-            int64_t ldQ, int b, double c, double* out, int64_t ldo, int variant) {
+            int64_t ldQ, int b, double c, double* out, int64_t ldo, int variant, bool use_lo) {
   (void)I;
   c /= (double)R.scale;
-  if (use_tc(variant, b)) { prod_t_tc(ctx, ws, R, ldI, J, Q, ldQ, b, c, out, ldo); return; }
+  if (use_tc(variant, b)) { prod_t_tc(ctx, ws, R, ldI, J, Q, ldQ, b, c, out, ldo, use_lo); return; }
   const int BK = b <= 32 ? 32 : 64;
   const int bp = (int)round_up(b, BK);
   convert_operand(ctx, ws, ldI, b, bp, Q, ldQ);   // Q has ldI rows (pad rows are zero)

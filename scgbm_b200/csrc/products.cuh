@@ -54,14 +54,14 @@ void prod_n(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t I, int64_t ldI, int64_t J,
             int64_t ldP, int b, double c, double* out, int64_t ldo, int variant, bool use_lo = true);
 
 void prod_t(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t I, int64_t ldI, int64_t J, const double* Q,
-            int64_t ldQ, int b, double c, double* out, int64_t ldo, int variant);
+            int64_t ldQ, int b, double c, double* out, int64_t ldo, int variant, bool use_lo = true);
 
 // tcgen05 implementations (products_tc.cu); b <= 64
 bool prod_tc_supported(int b);
 void prod_n_tc(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t ldI, int64_t J, const double* P, int64_t ldP,
                int b, double c, double* out, int64_t ldo, bool use_lo);
 void prod_t_tc(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t ldI, int64_t J, const double* Q, int64_t ldQ,
-               int b, double c, double* out, int64_t ldo);
+               int b, double c, double* out, int64_t ldo, bool use_lo);
 void prod_n_reduce_launch(Ctx& ctx, int nchunk, int64_t ldI, int b, int bp, const double* part, double c,
                           const float* c_dev /* optional extra device factor */, double* out, int64_t ldo);
 

@@ -382,7 +382,7 @@ void prod_n_tc(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t ldI, int64_t J, const d
 }
 
 void prod_t_tc(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t ldI, int64_t J, const double* Q, int64_t ldQ,
-               int b, double c, double* out, int64_t ldo) {
+               int b, double c, double* out, int64_t ldo, bool use_lo) {
   SCGBM_REQUIRE(prod_tc_supported(b), "prod_t_tc: block too wide");
   const int bp = b <= 32 ? 32 : 64;
   split_operand(ctx, ws, ldI, b, bp, ldI, Q, ldQ);
@@ -392,7 +392,7 @@ void prod_t_tc(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t ldI, int64_t J, const d
   p.n_gene_tiles = 1;
   p.n_tiles = (int)ceil_div(J, 128);
   p.kb_t = (int)(ldI / TC_KB);
-  p.c = c; p.out = out; p.ldo = ldo; p.op_inv_scale = ws.opmeta.get() + 1; p.use_lo = 1;
+  p.c = c; p.out = out; p.ldo = ldo; p.op_inv_scale = ws.opmeta.get() + 1; p.use_lo = use_lo ? 1 : 0;
   const CUtensorMap mh = make_tmap_2d(R.hi, 2, false, (uint64_t)ldI, (uint64_t)J, (uint64_t)ldI * 2, 64, 64);
   const CUtensorMap ml = make_tmap_2d(R.lo, 2, false, (uint64_t)ldI, (uint64_t)J, (uint64_t)ldI * 2, 64, 64);
   const CUtensorMap mb = make_tmap_2d(ws.op16.get(), 2, false, (uint64_t)ldI, (uint64_t)(2 * bp), (uint64_t)ldI * 2, 64, 2 * bp);

@@ -121,7 +121,7 @@ static void op_mul(Ctx& ctx, TsvdWs& ws, const GOperator& op, const double* P, i
     }
     ts_mul(ctx, op.ldI, lt.M, b, lt.A, lt.lda, C, lt.M, out, op.ldI, 1.0, 1.0);
   }
-  if (op.R.hi && op.c != 0.0) prod_n(ctx, ws.prod, op.R, op.I, op.ldI, op.J, P, ldP, b, op.c, out, op.ldI, variant, !hi_only);
+  if (op.R.hi && op.c != 0.0) prod_n(ctx, ws.prod, op.R, op.I, op.ldI, op.J, P, ldP, b, op.c, out, op.ldI, variant, !(hi_only || ws.lowprec));
   ctx.allreduce_sum(out, op.ldI * b);
 }
 
@@ -141,7 +141,7 @@ static void op_tmul(Ctx& ctx, TsvdWs& ws, const GOperator& op, const double* Q, 
     }
     ts_mul(ctx, op.J, lt.M, b, lt.B, lt.ldb, C, lt.M, out, op.ldJ, 1.0, 1.0);
   }
-  if (op.R.hi && op.c != 0.0) prod_t(ctx, ws.prod, op.R, op.I, op.ldI, op.J, Q, ldQ, b, op.c, out, op.ldJ, variant);
+  if (op.R.hi && op.c != 0.0) prod_t(ctx, ws.prod, op.R, op.I, op.ldI, op.J, Q, ldQ, b, op.c, out, op.ldJ, variant, !ws.lowprec);
 }
 
 static void tsvd_alloc(TsvdWs& ws, int64_t ldI, int64_t ldJ, int b, int pmax, int maxM) {
@@ -215,6 +215,12 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
       V0 = ws.Vb.get();
     }
     int p = b;
+    // A cold start spends most of its cycles far from convergence: until the estimate is within
+    // 30x of the tolerance the products read only the hi plane of the residual (an 11-bit
+    // operator, half the bytes); the remaining cycles run on the full operator and are the
+    // only ones allowed to declare convergence.
+    static const bool no_lowprec = getenv("SCGBM_COLD_FULL") != nullptr;
+    ws.lowprec = !was_warm && !no_lowprec;
     for (int cycle = 0; !restart; ++cycle) {
       ws.T.zero(ctx.stream);
       op_mul(ctx, ws, op, V0, ldJ, b, ws.Qb.get(), o.variant);
@@ -277,7 +283,11 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
       ts_mul(ctx, op.J, p, b, ws.Zb.get(), ldJ, ws.C.get(), p, ws.Vwarm.get(), ldJ, 1.0, 0.0);
       static const bool trace = getenv("SCGBM_TRACE") != nullptr;
       if (trace) fprintf(stderr, "[scgbm-trace]   tsvd %s cycle %d: p=%d passes so far %d est %.3e\n", was_warm ? "warm" : "cold", cycle, p, passes, est);
-      const bool converged = est < o.tol || depth == 0;
+      bool converged = est < o.tol || depth == 0;
+      if (ws.lowprec) {
+        if (est < 30.0 * o.tol || cycle + 5 >= o.max_cycles) ws.lowprec = false;
+        converged = false;
+      }
       if (converged || cycle + 1 >= o.max_cycles || (was_warm && cycle >= 1)) break;
       V0 = ws.Vwarm.get();
     }
@@ -286,6 +296,7 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
     ws.robust = true;   // the operator family of this fit is rank deficient: stay robust
   }
   ws.warm = true;
+  ws.lowprec = false;
   if (fast_call) ++ws.fast_streak;
   else { ws.fast_streak = 0; ws.last_est = est; }
   copy_mat(ctx, ldI, M, ws.Ub.get(), ldI, outU, ldI);

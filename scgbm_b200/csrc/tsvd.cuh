@@ -52,6 +52,7 @@ struct TsvdWs {
   int64_t passes_total = 0, calls = 0;
   double last_est = 1e300;  // residual estimate of the last call that ran a Krylov extension
   int fast_streak = 0;      // consecutive calls that skipped the extension
+  bool lowprec = false;     // cold start, early cycles: products read only the residual's hi plane
 };
 
 // outU: ldI x M, outD: M, outV: ldJ x M (device, column-major)
