@@ -102,7 +102,7 @@ __global__ void ritz_scale_kernel(int p, int b, const double* __restrict__ S, co
 
 // ---------------------------------------------------------------------------------
 static void op_mul(Ctx& ctx, TsvdWs& ws, const GOperator& op, const double* P, int64_t ldP, int b, double* out,
-                   int variant) {
+                   int variant, bool start_block = false) {
   // experiment knob (off): read only the residual's hi plane in G P.  Measured: the Krylov space
   // of the perturbed operator loses the true singular vectors at first order (angles 2e-4,
   // objective 2e-6) -- outside the parity tolerances, so both planes are always used.
@@ -121,7 +121,7 @@ static void op_mul(Ctx& ctx, TsvdWs& ws, const GOperator& op, const double* P, i
     }
     ts_mul(ctx, op.ldI, lt.M, b, lt.A, lt.lda, C, lt.M, out, op.ldI, 1.0, 1.0);
   }
-  if (op.R.hi && op.c != 0.0) prod_n(ctx, ws.prod, op.R, op.I, op.ldI, op.J, P, ldP, b, op.c, out, op.ldI, variant, !(hi_only || ws.lowprec));
+  if (op.R.hi && op.c != 0.0) prod_n(ctx, ws.prod, op.R, op.I, op.ldI, op.J, P, ldP, b, op.c, out, op.ldI, variant, !(hi_only || ws.lowprec || (start_block && ws.start_hi)));
   ctx.allreduce_sum(out, op.ldI * b);
 }
 
@@ -221,9 +221,15 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
     // only ones allowed to declare convergence.
     static const bool no_lowprec = getenv("SCGBM_COLD_FULL") != nullptr;
     ws.lowprec = !was_warm && !no_lowprec;
+    // Warm calls: the start block Q0 = orth(G V0) may come from the 11-bit operator (hi plane only,
+    // half the bytes): Q1 = orth(G Z0 _|_ Q0) and Z = G^T Q use the full operator, so span{Q0, Q1} is
+    // still an exact Krylov space of G G^T, merely started 2^-12-relative away from G V0 -- measured
+    // parity-neutral (objective, alpha, angles unchanged to the digits printed), unlike hi-only Q1.
+    static const bool env_start_full = getenv("SCGBM_START_FULL") != nullptr;
+    ws.start_hi = was_warm && !env_start_full;
     for (int cycle = 0; !restart; ++cycle) {
       ws.T.zero(ctx.stream);
-      op_mul(ctx, ws, op, V0, ldJ, b, ws.Qb.get(), o.variant);
+      op_mul(ctx, ws, op, V0, ldJ, b, ws.Qb.get(), o.variant, true);
       ++passes;
       sym_orth(ctx, ws.small, ldI, b, ws.Qb.get(), ldI, nullptr, ldI, 0, ws.tmpI.get(), robust, ws.flag.get());
       for (int t = 0;; ++t) {

@@ -53,6 +53,7 @@ struct TsvdWs {
   double last_est = 1e300;  // residual estimate of the last call that ran a Krylov extension
   int fast_streak = 0;      // consecutive calls that skipped the extension
   bool lowprec = false;     // cold start, early cycles: products read only the residual's hi plane
+  bool start_hi = false;    // warm call: the start block Q0 = orth(G V0) is built from the hi plane only
 };
 
 // outU: ldI x M, outD: M, outV: ldJ x M (device, column-major)
