@@ -2,6 +2,7 @@
 // replaces irlba::irlba (R/fit.R:115,323): tall-skinny Gram / multiply kernels, a
 // single-CTA parallel Jacobi symmetric eigensolver, and the orthonormalisation built
 // from them.  Everything stays on the device; the host only sequences launches.
+#include <cooperative_groups.h>
 #include "dense_small.cuh"
 
 namespace scgbm {
@@ -318,8 +319,148 @@ jacobi_eigh_kernel(int n, double* __restrict__ Ag, double* __restrict__ Vg, doub
   }
 }
 
+// ---------------------------------------------------------------------------------
+// The same cyclic Jacobi for matrices too large for one CTA's shared memory (n > 128: the
+// cold-start Ritz problems, p = 5b up to 320 at M = 50): a cooperative grid, one grid-wide
+// barrier per rotation round.  A and V ping-pong between two global (L2-resident) buffers:
+// every CTA derives the round's n/2 rotations redundantly from the OLD buffer, then the grid
+// rewrites each 2 x 2 block  B' = J_r^T B J_c  (and each column pair of V) into the NEW one,
+// so no CTA ever reads what another is writing.  Odd n is padded with a zero row/column whose
+// rotations are identities.
+// ---------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+
+__global__ void jacobi_coop_init_kernel(int n, int m, const double* __restrict__ A, double* __restrict__ A0,
+                                        double* __restrict__ V0) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m * m) return;
+  const int i = idx % m, j = idx / m;
+  A0[idx] = (i < n && j < n) ? A[(size_t)j * n + i] : 0.0;
+  V0[idx] = (i == j) ? 1.0 : 0.0;
+}
+
+__global__ void __launch_bounds__(256)
+jacobi_coop_kernel(int n, int m, double* __restrict__ Abuf0, double* __restrict__ Abuf1, double* __restrict__ Vbuf0,
+                   double* __restrict__ Vbuf1, double* __restrict__ w, double* __restrict__ Vout, int max_sweeps) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ double smj[];
+  const int half = m / 2;
+  double* cs = smj;                 // [half]
+  double* sn = cs + half;           // [half]
+  double* red = sn + half;          // [32]
+  int* pp = reinterpret_cast<int*>(red + 32);   // [half] p
+  int* qq = pp + half;                          // [half] q
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t gsize = (int64_t)gridDim.x * blockDim.x;
+  double* Ab[2] = {Abuf0, Abuf1};
+  double* Vb[2] = {Vbuf0, Vbuf1};
+  int cur = 0;
+  double fro2 = 0.0;
+  for (int sweep = 0; sweep <= max_sweeps; ++sweep) {
+    // every CTA evaluates the same convergence test on the same data
+    const double* A = Ab[cur];
+    double off = 0.0, all = 0.0;
+    for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
+      const double a = A[idx];
+      all += a * a;
+      if (idx % m != idx / m) off += a * a;
+    }
+    const double off2 = block_sum_1024(off, red);
+    if (sweep == 0) fro2 = block_sum_1024(all, red);
+    if (off2 <= 1e-28 * fro2 || fro2 == 0.0 || sweep == max_sweeps) break;
+    for (int r = 0; r < m - 1; ++r) {
+      const double* Ao = Ab[cur];
+      const double* Vo = Vb[cur];
+      double* An = Ab[cur ^ 1];
+      double* Vn = Vb[cur ^ 1];
+      for (int k = threadIdx.x; k < half; k += blockDim.x) {
+        int p, q;
+        jacobi_pair(r, k, m, p, q);
+        double c = 1.0, s = 0.0;
+        const double apq = Ao[(size_t)q * m + p];
+        const double app = Ao[(size_t)p * m + p], aqq = Ao[(size_t)q * m + q];
+        if (fabs(apq) > 1e-300 && fabs(apq) > 1e-17 * sqrt(fabs(app * aqq))) {
+          const double tau = (aqq - app) / (2.0 * apq);
+          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c = rsqrt(1.0 + t * t);
+          s = t * c;
+        }
+        cs[k] = c; sn[k] = s; pp[k] = p; qq[k] = q;
+      }
+      __syncthreads();
+      const int64_t nblk = (int64_t)half * half;
+      for (int64_t item = gtid; item < nblk + (int64_t)half * m; item += gsize) {
+        if (item < nblk) {        // A: rows (pr, qr) x columns (pc, qc)
+          const int kr = (int)(item % half), kc = (int)(item / half);
+          const int pr = pp[kr], qr = qq[kr], pc = pp[kc], qc = qq[kc];
+          const double cr = cs[kr], sr = sn[kr], cc = cs[kc], sc = sn[kc];
+          const double b00 = Ao[(size_t)pc * m + pr], b10 = Ao[(size_t)pc * m + qr];
+          const double b01 = Ao[(size_t)qc * m + pr], b11 = Ao[(size_t)qc * m + qr];
+          const double t00 = cc * b00 - sc * b01, t01 = sc * b00 + cc * b01;
+          const double t10 = cc * b10 - sc * b11, t11 = sc * b10 + cc * b11;
+          An[(size_t)pc * m + pr] = cr * t00 - sr * t10;
+          An[(size_t)pc * m + qr] = sr * t00 + cr * t10;
+          An[(size_t)qc * m + pr] = cr * t01 - sr * t11;
+          An[(size_t)qc * m + qr] = sr * t01 + cr * t11;
+        } else {                  // V: column pair kc, one row
+          const int64_t it2 = item - nblk;
+          const int i = (int)(it2 % m), kc = (int)(it2 / m);
+          const int pc = pp[kc], qc = qq[kc];
+          const double c = cs[kc], s2 = sn[kc];
+          const double x = Vo[(size_t)pc * m + i], y = Vo[(size_t)qc * m + i];
+          Vn[(size_t)pc * m + i] = c * x - s2 * y;
+          Vn[(size_t)qc * m + i] = s2 * x + c * y;
+        }
+      }
+      grid.sync();
+      cur ^= 1;
+    }
+  }
+  // sort eigenvalues descending (rank by counting) and write out; the pad index n never mixes
+  const double* A = Ab[cur];
+  const double* V = Vb[cur];
+  const int gwarp = (int)(gtid >> 5), nwarps = (int)(gsize >> 5), lane = threadIdx.x & 31;
+  for (int i = gwarp; i < n; i += nwarps) {
+    const double di = A[(size_t)i * m + i];
+    int rank = 0;
+    for (int j = lane; j < n; j += 32) {
+      const double dj = A[(size_t)j * m + j];
+      if (dj > di || (dj == di && j < i)) ++rank;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+    if (lane == 0) w[rank] = di;
+    for (int k = lane; k < n; k += 32) Vout[(size_t)rank * n + k] = V[(size_t)i * m + k];
+  }
+}
+
+static void eigh_desc_coop(Ctx& ctx, SmallWs& ws, int n, double* A, double* w, double* Vout) {
+  int m = (n % 2 == 0) ? n : n + 1;
+  const int half = m / 2;
+  ws.need_eigV(4 * (int64_t)m * m);
+  double* A0 = ws.eigV.get();
+  double* A1 = A0 + (size_t)m * m;
+  double* V0 = A1 + (size_t)m * m;
+  double* V1 = V0 + (size_t)m * m;
+  ProfScope ps(ctx.prof, SCGBM_K_SMALL, 2);
+  jacobi_coop_init_kernel<<<(unsigned)ceil_div((int64_t)m * m, 256), 256, 0, ctx.stream>>>(n, m, A, A0, V0);
+  SCGBM_LAUNCH_CHECK();
+  const size_t smem = (size_t)(2 * half + 32) * sizeof(double) + (size_t)2 * half * sizeof(int) + 16;
+  int per_sm = 0;
+  SCGBM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_coop_kernel, 256, smem));
+  SCGBM_REQUIRE(per_sm >= 1, "eigh_desc: cooperative Jacobi does not fit");
+  const int64_t items = (int64_t)half * half + (int64_t)half * m;
+  int grid = (int)std::min<int64_t>((int64_t)ctx.num_sms * std::min(per_sm, 2), ceil_div(items, 256));
+  grid = std::max(grid, 1);
+  int max_sweeps = 40;
+  void* args[] = {&n, &m, &A0, &A1, &V0, &V1, &w, &Vout, &max_sweeps};
+  SCGBM_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_coop_kernel, dim3(grid), dim3(256), args, smem, ctx.stream));
+}
+
 void eigh_desc(Ctx& ctx, SmallWs& ws, int n, double* A, double* w, double* Vout) {
   SCGBM_REQUIRE(n >= 1 && n <= 1024, "eigh_desc: n out of range");
+  static const int coop_from = getenv("SCGBM_JACOBI_COOP_FROM") ? atoi(getenv("SCGBM_JACOBI_COOP_FROM")) : 129;
+  if (n >= coop_from) { eigh_desc_coop(ctx, ws, n, A, w, Vout); return; }
   const int m = (n % 2 == 0) ? n : n + 1;
   const int lds = n | 1;
   const size_t base = (size_t)(m + 32) * sizeof(double) + (size_t)((m / 2 + 1) & ~1) * sizeof(int) + 16;

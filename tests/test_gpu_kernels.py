@@ -13,7 +13,7 @@ def lib():
     return L.load()
 
 
-@pytest.mark.parametrize("n", [1, 2, 5, 31, 32, 44, 63, 96, 97, 128, 180])
+@pytest.mark.parametrize("n", [1, 2, 5, 31, 32, 44, 63, 96, 97, 128, 180, 129, 160, 311])
 def test_eigh_matches_lapack(lib, n):
     from scgbm_b200 import _lib as L
     rng = np.random.default_rng(n)
