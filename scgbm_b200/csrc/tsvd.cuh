@@ -31,7 +31,7 @@ struct TsvdOpts {
   int M = 0;
   int extra = 12;       // block = M + extra
   int depth = 3;        // Krylov extensions per cycle (warm start)
-  int cold_depth = 4;   // ... on a cold start: p = 5b = 160 keeps the Jacobi matrix in shared memory
+  int cold_depth = 7;   // ... on a cold start (fewer, deeper cycles; the p = 8b Ritz problem runs on the cooperative Jacobi)
   double tol = 1e-4;    // Ritz residual estimate
   int max_cycles = 40;  // restarts (cold start on gap-less spectra)
   uint64_t seed = 0;
