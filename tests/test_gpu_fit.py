@@ -56,6 +56,19 @@ def test_readme_get_se(readme_Y, readme_oracle_fit):
     np.testing.assert_allclose(eps["se_scores"], o_get_se(readme_oracle_fit, EPS=0.001)["se_scores"], rtol=1e-10)
 
 
+def test_golden_fixture():
+    """CUDA path against committed oracle vectors (scripts/make_golden.py): no oracle at run time."""
+    from scgbm_b200 import gbm_sc, get_se
+    G = np.load(os.path.join(GOLD, "sim_nb_257x1031.npz"))
+    out = get_se(gbm_sc(G["Y"], int(G["M"]), infer_beta=bool(G["infer_beta"]), diagnostics=True))
+    ref = {k: G[k] for k in ("alpha", "beta", "U", "V", "D", "scores", "obj")}
+    ref["_LL"] = G["LL"]; ref["_accepted"] = G["accepted"]; ref["_n_iter"] = int(G["n_iter"])
+    assert assert_fit_parity(ref, out, check_W=False) in ("full", "knife-edge")
+    if int(G["n_iter"]) == out["_n_iter"]:
+        np.testing.assert_allclose(out["se_scores"], G["se_scores"], rtol=1e-3)
+        np.testing.assert_allclose(out["se_loadings"], G["se_loadings"], rtol=1e-3)
+
+
 CASES = [
     # I, J, d(sim), M, kwargs, generator kwargs
     (300, 400, 5, 5, dict(), dict(nb=None)),

@@ -28,3 +28,14 @@ def test_readme_se_head(readme_oracle_fit):
     se = get_se(readme_oracle_fit)["se_scores"][:6]
     # reference used irlba(tol=1e-5); the README prints 7 digits
     np.testing.assert_allclose(se, np.array(G["se_scores_head"]), rtol=0, atol=5e-6)
+
+
+def test_oracle_reproduces_committed_fixture():
+    """tests/golden/sim_nb_257x1031.npz (scripts/make_golden.py) is what the oracle computes today."""
+    from oracle.scgbm_oracle import gbm_sc
+    F = np.load(os.path.join(os.path.dirname(__file__), "golden", "sim_nb_257x1031.npz"))
+    out = gbm_sc(F["Y"], int(F["M"]), infer_beta=bool(F["infer_beta"]))
+    assert out["_n_iter"] == int(F["n_iter"])
+    np.testing.assert_array_equal(out["_accepted"], F["accepted"])
+    np.testing.assert_allclose(out["_LL"], F["LL"], rtol=1e-12)
+    np.testing.assert_allclose(out["alpha"], F["alpha"], atol=1e-10)
