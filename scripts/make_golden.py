@@ -15,11 +15,13 @@ sys.path.insert(0, ROOT)
 from oracle import scgbm_oracle as O  # noqa: E402
 
 Y = O.sim_data(257, 1031, 8, seed=257 + 1031, nb_theta=1.0)["Y"]
-ref = O.get_se_fast(O.gbm_sc(Y, 8, infer_beta=True))
+ref = O.gbm_sc(Y, 8, infer_beta=True)
+ref["W"] = ref["W"].astype(np.float32).astype(np.float64)     # stored as float32: get.se is evaluated on exactly this W
+ref = O.get_se_fast(ref)
 np.savez_compressed(
     os.path.join(ROOT, "tests", "golden", "sim_nb_257x1031.npz"),
     Y=Y.astype(np.int32), M=8, infer_beta=True,
     LL=ref["_LL"], accepted=ref["_accepted"], obj=ref["obj"], n_iter=ref["_n_iter"],
     alpha=ref["alpha"], beta=ref["beta"], U=ref["U"], V=ref["V"], D=ref["D"], scores=ref["scores"],
-    se_scores=ref["se_scores"], se_loadings=ref["se_loadings"])
+    W=ref["W"].astype(np.float32), se_scores=ref["se_scores"], se_loadings=ref["se_loadings"])
 print("wrote tests/golden/sim_nb_257x1031.npz", Y.shape, ref["_n_iter"], "iterations")

@@ -60,13 +60,14 @@ def test_golden_fixture():
     """CUDA path against committed oracle vectors (scripts/make_golden.py): no oracle at run time."""
     from scgbm_b200 import gbm_sc, get_se
     G = np.load(os.path.join(GOLD, "sim_nb_257x1031.npz"))
-    out = get_se(gbm_sc(G["Y"], int(G["M"]), infer_beta=bool(G["infer_beta"]), diagnostics=True))
+    out = gbm_sc(G["Y"], int(G["M"]), infer_beta=bool(G["infer_beta"]), diagnostics=True)
     ref = {k: G[k] for k in ("alpha", "beta", "U", "V", "D", "scores", "obj")}
     ref["_LL"] = G["LL"]; ref["_accepted"] = G["accepted"]; ref["_n_iter"] = int(G["n_iter"])
     assert assert_fit_parity(ref, out, check_W=False) in ("full", "knife-edge")
-    if int(G["n_iter"]) == out["_n_iter"]:
-        np.testing.assert_allclose(out["se_scores"], G["se_scores"], rtol=1e-3)
-        np.testing.assert_allclose(out["se_loadings"], G["se_loadings"], rtol=1e-3)
+    # get.se on the fixture's own fit (per-factor SEs are only comparable for identical U, scores, W)
+    se = get_se({"U": G["U"], "scores": G["scores"], "D": G["D"], "W": G["W"].astype(np.float64)})
+    np.testing.assert_allclose(se["se_scores"], G["se_scores"], rtol=1e-8)
+    np.testing.assert_allclose(se["se_loadings"], G["se_loadings"], rtol=1e-8)
 
 
 CASES = [
