@@ -111,6 +111,13 @@ typedef struct scgbm_fit_args {
   int32_t  verbose;
   scgbm_progress_cb progress; /* called once per accepted iteration (R/fit.R:175)   */
   void*    progress_user;
+  /* --- sparse input: used when Y == NULL.  Column-compressed like Matrix::dgCMatrix
+   * (the reference densifies such input itself, R/fit.R:224); the dense device matrix is built by a
+   * scatter kernel, so no I x J host copy ever exists. --- */
+  const int32_t* csc_i; /* nnz 0-based row indices          (dgCMatrix@i)                       */
+  const int64_t* csc_p; /* J + 1 column pointers            (dgCMatrix@p widened to 64 bit)     */
+  const void*    csc_x; /* nnz values                       (dgCMatrix@x: SCGBM_F64)            */
+  int32_t  csc_x_dtype; /* scgbm_dtype of csc_x                                                 */
 } scgbm_fit_args;
 
 typedef struct scgbm_fit_out {

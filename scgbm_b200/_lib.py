@@ -51,7 +51,8 @@ class FitArgs(C.Structure):
                 ("y_storage", C.c_int32), ("device", C.c_int32), ("comm", C.c_void_p),
                 ("svd_extra", C.c_int32), ("svd_depth", C.c_int32), ("svd_tol", C.c_double),
                 ("seed", C.c_uint64), ("profile", C.c_int32), ("verbose", C.c_int32),
-                ("progress", PROGRESS_CB), ("progress_user", C.c_void_p)]
+                ("progress", PROGRESS_CB), ("progress_user", C.c_void_p),
+                ("csc_i", C.c_void_p), ("csc_p", C.c_void_p), ("csc_x", C.c_void_p), ("csc_x_dtype", C.c_int32)]
 
 
 class FitOut(C.Structure):

@@ -42,6 +42,14 @@ def _as_counts(Y):
     return Y, _NP2DT[Y.dtype]
 
 
+def _is_sparse(Y):
+    try:
+        import scipy.sparse as sp
+        return sp.issparse(Y)
+    except Exception:       # pragma: no cover
+        return False
+
+
 def _batch_codes(batch, J):
     """R: `batch` must be a factor (R/fit.R:86-88); here: any 1-D array of labels.
     Returns 1-based int32 codes in order of first appearance of the SORTED levels
@@ -76,7 +84,17 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
                   file=sys.stderr)
         return out
     lib = L.load()
-    if y_device_ptr is not None:
+    csc = None
+    if _is_sparse(Y):
+        # Matrix::dgCMatrix-style input: handed over column-compressed, densified on the GPU
+        Ys = Y.tocsc()
+        I, J = Ys.shape
+        xs = np.ascontiguousarray(Ys.data)
+        if xs.dtype not in _NP2DT:
+            xs = xs.astype(np.float64)
+        csc = (np.ascontiguousarray(Ys.indices, dtype=np.int32), np.ascontiguousarray(Ys.indptr, dtype=np.int64), xs)
+        y_ptr, y_dt, on_dev, ldY, Yh = None, _NP2DT[xs.dtype], 0, I, None
+    elif y_device_ptr is not None:
         I, J = y_device_shape
         y_ptr, y_dt, on_dev, ldY = C.c_void_p(y_device_ptr), y_device_dtype, 1, ((I + 63) // 64) * 64
         Yh = None
@@ -113,6 +131,8 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
     a.svd_extra = int(svd_extra); a.svd_depth = int(svd_depth); a.svd_tol = float(svd_tol)
     a.seed = int(seed); a.profile = int(bool(profile)); a.verbose = int(bool(verbose))
     a.progress = cb; a.progress_user = None
+    if csc is not None:
+        a.csc_i = L.ptr(csc[0]); a.csc_p = L.ptr(csc[1]); a.csc_x = L.ptr(csc[2]); a.csc_x_dtype = y_dt
     o = L.FitOut()
     o.U = L.ptr(U); o.D = L.ptr(D); o.V = L.ptr(V); o.loadings = L.ptr(loadings); o.scores = L.ptr(scores)
     o.alpha = L.ptr(alpha); o.beta = L.ptr(beta); o.obj = L.ptr(obj); o.time = L.ptr(tvec)

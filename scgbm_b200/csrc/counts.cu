@@ -236,6 +236,125 @@ static void load_impl(Ctx& ctx, const void* Y, int y_dtype, int y_on_device, int
   }
 }
 
+// ---------------------------------------------------------------------------------
+// sparse ingest: one warp per column scatters its non-zeros into the (zeroed) dense device matrix
+// ---------------------------------------------------------------------------------
+template <typename Tx, typename Tout>
+__global__ void csc_scatter_kernel(int64_t I, int64_t ld, int64_t jc, const int64_t* __restrict__ p /* jc + 1, chunk-relative base p[0] */,
+                                   const int32_t* __restrict__ ri, const Tx* __restrict__ x, Tout* __restrict__ out,
+                                   PackStats* __restrict__ st) {
+  const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (j >= jc) return;
+  const int64_t base = p[0], a = p[j] - base, b = p[j + 1] - base;
+  int flags = 0;
+  for (int64_t k = a + lane; k < b; k += 32) {
+    const int32_t i = ri[k];
+    double v = (double)x[k];
+    if (i < 0 || i >= I) { flags |= 16; continue; }
+    if (v != v) { flags |= 2; v = 0.0; }
+    if (v < 0.0) flags |= 1;
+    if (OutLimit<Tout>::integral && v != floor(v)) flags |= 4;
+    if (v > OutLimit<Tout>::max) flags |= 8;
+    out[j * ld + i] = (Tout)v;
+  }
+  if (flags) atomicOr(&st->flags, flags);
+}
+
+template <typename Tout>
+static void launch_scatter(cudaStream_t s, int x_dtype, int64_t I, int64_t ld, int64_t jc, const int64_t* p,
+                           const int32_t* ri, const void* x, void* out, PackStats* st) {
+  const unsigned grid = (unsigned)ceil_div(jc * 32, 256);
+  switch (x_dtype) {
+    case SCGBM_F64: csc_scatter_kernel<double, Tout><<<grid, 256, 0, s>>>(I, ld, jc, p, ri, (const double*)x, (Tout*)out, st); break;
+    case SCGBM_F32: csc_scatter_kernel<float, Tout><<<grid, 256, 0, s>>>(I, ld, jc, p, ri, (const float*)x, (Tout*)out, st); break;
+    case SCGBM_I32: csc_scatter_kernel<int32_t, Tout><<<grid, 256, 0, s>>>(I, ld, jc, p, ri, (const int32_t*)x, (Tout*)out, st); break;
+    case SCGBM_U16: csc_scatter_kernel<uint16_t, Tout><<<grid, 256, 0, s>>>(I, ld, jc, p, ri, (const uint16_t*)x, (Tout*)out, st); break;
+    case SCGBM_U8: csc_scatter_kernel<uint8_t, Tout><<<grid, 256, 0, s>>>(I, ld, jc, p, ri, (const uint8_t*)x, (Tout*)out, st); break;
+    default: throw Error(SCGBM_ERR_INVALID, "unknown csc_x_dtype");
+  }
+  SCGBM_LAUNCH_CHECK();
+}
+
+void load_counts_csc(Ctx& ctx, const int32_t* csc_i, const int64_t* csc_p, const void* csc_x, int x_dtype,
+                     int64_t I, int64_t J, const int32_t* batch_host, int nbatch, int storage_req, Counts& c) {
+  SCGBM_REQUIRE(csc_i && csc_p && csc_x, "sparse input needs csc_i, csc_p and csc_x");
+  SCGBM_REQUIRE(I >= 1 && J >= 1 && nbatch >= 1, "Y must have at least one row and one column");
+  SCGBM_REQUIRE(csc_p[0] >= 0, "csc_p must be non-decreasing");
+  for (int64_t j = 0; j < J; ++j) SCGBM_REQUIRE(csc_p[j + 1] >= csc_p[j], "csc_p must be non-decreasing");
+  c.I = I; c.J = J; c.ld = round_up(I, kRowPad); c.nbatch = nbatch;
+  c.colsum.alloc(J);
+  c.rowsum.alloc(c.ld * nbatch);
+  if (batch_host && nbatch > 1) {
+    std::vector<int32_t> b0(J);
+    for (int64_t j = 0; j < J; ++j) {
+      SCGBM_REQUIRE(batch_host[j] >= 1 && batch_host[j] <= nbatch, "batch codes must be in 1..nbatch");
+      b0[j] = batch_host[j] - 1;
+    }
+    c.batch.alloc(J);
+    SCGBM_CUDA(cudaMemcpyAsync(c.batch.get(), b0.data(), J * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
+    SCGBM_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+  DevBuf<PackStats> st(1);
+  const int xb = dtype_bytes(x_dtype);
+  // column chunks of at most ~32M non-zeros (and at least one column)
+  const int64_t max_nnz = 32ll << 20;
+  int storage = storage_req == SCGBM_STORE_AUTO ? SCGBM_STORE_U16 : storage_req;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    c.storage = storage;
+    c.owned.alloc(c.ld * J * c.elem_bytes());
+    c.data = c.owned.get();
+    SCGBM_CUDA(cudaMemsetAsync(c.data, 0, (size_t)c.ld * J * c.elem_bytes(), ctx.stream));
+    c.colsum.zero(ctx.stream); c.rowsum.zero(ctx.stream); st.zero(ctx.stream);
+    DevBuf<int64_t> dp;
+    DevBuf<int32_t> di;
+    DevBuf<uint8_t> dx;
+    for (int64_t j0 = 0; j0 < J;) {
+      int64_t j1 = j0 + 1;
+      while (j1 < J && csc_p[j1 + 1] - csc_p[j0] <= max_nnz && j1 - j0 < (1 << 22)) ++j1;
+      const int64_t jc = j1 - j0, n0 = csc_p[j0], nn = csc_p[j1] - n0;
+      if (dp.n < jc + 1) dp.alloc(jc + 1);
+      if (di.n < nn) { di.alloc(std::max<int64_t>(nn, 1)); dx.alloc(std::max<int64_t>(nn, 1) * xb); }
+      SCGBM_CUDA(cudaMemcpyAsync(dp.get(), csc_p + j0, (jc + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx.stream));
+      if (nn > 0) {
+        SCGBM_CUDA(cudaMemcpyAsync(di.get(), csc_i + n0, nn * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
+        SCGBM_CUDA(cudaMemcpyAsync(dx.get(), (const uint8_t*)csc_x + (size_t)n0 * xb, (size_t)nn * xb, cudaMemcpyHostToDevice, ctx.stream));
+        ctx.prof.h2d_bytes += (double)nn * (4 + xb) + (double)(jc + 1) * 8;
+        ProfScope ps(ctx.prof, SCGBM_K_PACK, 1);
+        void* out = (uint8_t*)c.data + (size_t)j0 * c.ld * c.elem_bytes();
+        switch (storage) {
+          case SCGBM_STORE_U8: launch_scatter<uint8_t>(ctx.stream, x_dtype, I, c.ld, jc, dp.get(), di.get(), dx.get(), out, st.get()); break;
+          case SCGBM_STORE_U16: launch_scatter<uint16_t>(ctx.stream, x_dtype, I, c.ld, jc, dp.get(), di.get(), dx.get(), out, st.get()); break;
+          default: launch_scatter<float>(ctx.stream, x_dtype, I, c.ld, jc, dp.get(), di.get(), dx.get(), out, st.get()); break;
+        }
+      }
+      SCGBM_CUDA(cudaStreamSynchronize(ctx.stream));   // the staging buffers are reused by the next chunk
+      j0 = j1;
+    }
+    {   // exact integer statistics from the dense device matrix (same kernel as the dense path, stats only)
+      ProfScope ps(ctx.prof, SCGBM_K_PACK, 1);
+      const int native_dtype = storage == SCGBM_STORE_U8 ? SCGBM_U8 : (storage == SCGBM_STORE_U16 ? SCGBM_U16 : SCGBM_F32);
+      pack_dispatch(ctx, ctx.stream, storage, native_dtype, c.data, c.ld, nullptr, I, c.ld, J, c.data, c.batch.get(),
+                    c.colsum.get(), c.rowsum.get(), st.get(), 0);
+    }
+    PackStats h;
+    SCGBM_CUDA(cudaMemcpyAsync(&h, st.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
+    SCGBM_CUDA(cudaStreamSynchronize(ctx.stream));
+    if (h.flags & 16) throw Error(SCGBM_ERR_INVALID, "sparse Y: row index out of range");
+    if (h.flags & 2) throw Error(SCGBM_ERR_INVALID, "Count matrix Y cannot contain NA values.");
+    if (h.flags & 1) throw Error(SCGBM_ERR_INVALID, "Count matrix Y cannot contain negative values.");
+    if (h.flags & (4 | 8)) {
+      if (storage_req == SCGBM_STORE_AUTO && storage != SCGBM_STORE_F32) { storage = SCGBM_STORE_F32; continue; }
+      throw Error(SCGBM_ERR_INVALID, "Y does not fit the requested device storage format");
+    }
+    long long bits = (long long)h.max_bits;
+    double mx;
+    memcpy(&mx, &bits, sizeof(mx));
+    c.maxY = mx;
+    return;
+  }
+}
+
 void load_counts(Ctx& ctx, const void* Y, int y_dtype, int y_on_device, int64_t I, int64_t J, int64_t ldY,
                  const int32_t* batch_host, int nbatch, int storage_req, Counts& c) {
   load_impl(ctx, Y, y_dtype, y_on_device, I, J, ldY, nullptr, I, batch_host, nbatch, storage_req, c);

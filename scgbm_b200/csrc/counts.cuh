@@ -26,6 +26,10 @@ struct Counts {
 void load_counts(Ctx& ctx, const void* Y, int y_dtype, int y_on_device, int64_t I, int64_t J,
                  int64_t ldY, const int32_t* batch_host, int nbatch, int storage_req, Counts& c);
 
+// the same from a column-compressed sparse matrix (host arrays; 0-based row indices, J + 1 pointers)
+void load_counts_csc(Ctx& ctx, const int32_t* csc_i, const int64_t* csc_p, const void* csc_x, int x_dtype,
+                     int64_t I, int64_t J, const int32_t* batch_host, int nbatch, int storage_req, Counts& c);
+
 // gather rows `ixs` of Y (all columns) into a packed Counts (projection path, R/fit.R:237)
 void load_counts_rows(Ctx& ctx, const void* Y, int y_dtype, int y_on_device, int64_t I_full,
                       int64_t J, int64_t ldY, const int64_t* ixs_host, int64_t Ik, Counts& c);

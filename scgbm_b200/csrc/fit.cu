@@ -253,7 +253,8 @@ struct FitState {
 
   void setup() {
     I = a.I; J = a.J; M = a.M; nbatch = a.batch ? std::max(1, a.nbatch) : 1;
-    load_counts(ctx, a.Y, a.y_dtype, a.y_on_device, I, J, a.ldY, a.batch, nbatch, a.y_storage, Y);
+    if (!a.Y && a.csc_p) load_counts_csc(ctx, a.csc_i, a.csc_p, a.csc_x, a.csc_x_dtype, I, J, a.batch, nbatch, a.y_storage, Y);
+    else load_counts(ctx, a.Y, a.y_dtype, a.y_on_device, I, J, a.ldY, a.batch, nbatch, a.y_storage, Y);
     ldI = Y.ld; ldJ = round_up(J, kRowPad);
     geom = PassGeom{I, J, ldI, ldJ, nbatch, Y.batch.get()};
     // global stats
@@ -648,6 +649,7 @@ struct FitRun {
 static void check_fit_args(const scgbm_fit_args* a) {
   SCGBM_REQUIRE(a, "NULL args");
   SCGBM_REQUIRE(a->I >= 1 && a->J >= 1, "Y must be a non-empty matrix");
+  SCGBM_REQUIRE(a->Y || (a->csc_p && a->csc_i && a->csc_x), "Y is NULL (pass a dense matrix or the csc_* arrays)");
   SCGBM_REQUIRE(a->M >= 1, "M must be >= 1");
   SCGBM_REQUIRE(a->max_iter >= 1, "max.iter must be >= 1");
 }
