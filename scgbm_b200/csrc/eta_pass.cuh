@@ -38,6 +38,7 @@ struct EtaWs {
   DevBuf<double> row_part;   // [chunks][nbatch][ldI]
   DevBuf<double> scal_part;  // [ctas][4]
   DevBuf<double> scal;       // [4]: sum_w, sum_ylogw, max_w, spare
+  DevBuf<float> gmask;       // exp(beta) masked to one batch (multi-batch row sums on tcgen05)
 };
 
 // S[i,k] = sum_{j in batch k} g_j * exp(X_ij)      (R/fit.R:129)   -> S (ldI x nbatch, fp64)
@@ -55,7 +56,7 @@ void pass_fused(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const Co
 // resid += coef * X_ij   (iterations 1-2: the clamped, non-low-rank X0 terms of G)
 void pass_addx(Ctx& ctx, const PassGeom& g, const XDesc& x, float coef, ResidBuf resid);
 
-// ---- tcgen05 versions (eta_tc.cu): single batch, u8/u16 counts, M <= 64 -------------------
+// ---- tcgen05 versions (eta_tc.cu): u8/u16 counts, M <= 64 (column sums: single batch) ------
 bool eta_tc_supported(const PassGeom& g, const XDesc& x, int y_storage /* -1: pass without Y */);
 // side 0 = genes [hi|hi|lo], side 1 = cells [hi|lo|hi]; value = U[r,k] * d[k] * rs[r]
 void stage_factor16(Ctx& ctx, Factor16& f, int64_t n_real, int64_t ld, int M, int side, const double* U,

@@ -1,4 +1,4 @@
-// eta_tc.cu -- K3/K4 on the 5th-generation tensor cores (single batch, u8/u16 counts).
+// eta_tc.cu -- K3/K4 on the 5th-generation tensor cores (u8/u16 counts, M <= 64, any number of batches).
 //
 // The eta tile X = A B^T (A: genes x M with d folded in, B: cells x M) comes out of tcgen05
 // UMMAs instead of 2M FFMAs per entry.  Each factor is scaled by a power of two and split in
@@ -99,10 +99,12 @@ struct FusedTcParams {
   const float* la_row; const float* lb_col;      // alpha_i, beta_j (fp32; clip correction only)
   const float* inv_a; const float* inv_b;        // device: 1 / factor scales
   float maxY, log_maxY, rscale;
+  const int32_t* batch;               // J zero-based batch codes (MB only)
+  const float* rowscale;              // ldI x nbatch X0 row scaling (MB + CLAMP only) or null
   double* scal_part;                  // [cta][4]
 };
 
-template <typename YT, bool CLAMP>
+template <typename YT, bool CLAMP, bool MB>
 __global__ void __launch_bounds__(FT_NT, 1)
 fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_constant__ CUtensorMap map_genes,
                 const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_hi,
@@ -230,6 +232,8 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
       const bool cell_ok = cell < p.J;
       const float gj = cell_ok ? __ldg(p.g_col + cell) * p.rscale : 0.0f;
       const float lbj = cell_ok ? __ldg(p.lb_col + cell) : 0.0f;
+      // multi-batch: alpha (hence f_i, la_i and the X0 row scaling) depends on the batch of this thread's cell
+      const int64_t boff = (MB && cell_ok) ? (int64_t)__ldg(p.batch + cell) * p.ldI : 0;
       for (int g = 0; g < ngt; ++g) {
         const int gene0 = (gt0 + g) * FT_GENES;
         tc::mbar_wait(&d_full[db], dph[db]);
@@ -259,7 +263,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
             yv[c][1] = make_uint4(0u, 0u, 0u, 0u);
           }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) fv[c][k] = __ldg(reinterpret_cast<const float4*>(p.f_row + gene0 + col) + k);
+          for (int k = 0; k < 4; ++k) fv[c][k] = __ldg(reinterpret_cast<const float4*>(p.f_row + boff + gene0 + col) + k);
         }
         tc::tmem_wait_ld();
         tc::fence_before_sync();
@@ -291,6 +295,11 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
           for (int k = 0; k < 4; ++k) { f[4 * k] = fv[c][k].x; f[4 * k + 1] = fv[c][k].y; f[4 * k + 2] = fv[c][k].z; f[4 * k + 3] = fv[c][k].w; }
           float tsw = 0.0f, tsyl = 0.0f, cm = 0.0f;
           float wv[16], r[16];
+          if (MB && CLAMP && p.rowscale) {                           // X0 with batches: per (gene, batch) scaling, R/fit.R:117
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+              xr[k] = __float_as_uint(__uint_as_float(xr[k]) * __ldg(p.rowscale + boff + gene0 + col + k));
+          }
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
             float xs = __uint_as_float(xr[k]);                        // sA sB x
@@ -309,7 +318,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
 #pragma unroll
             for (int k = 0; k < 16; ++k)
               if (wv[k] > maxYs && y[k] != 0.0f) {
-                const float lw = __uint_as_float(xr[k]) * inv + (__ldg(p.la_row + gene0 + col + k) + lbj);
+                const float lw = __uint_as_float(xr[k]) * inv + (__ldg(p.la_row + boff + gene0 + col + k) + lbj);
                 corr += (double)(y[k] * inv_rs) * (double)(p.log_maxY - lw);
               }
           }
@@ -396,6 +405,7 @@ struct RowsumTcParams {
   int nslab, kk;
   int n_gene_tiles, n_chunks, cell_tiles_per_chunk, n_cell_tiles;
   const float* g_col;   // exp(beta_j), zero padded to a multiple of 128 cells
+  const float* lane_scale;  // per-lane multiplier of x before the clamp (X0 with batches) or null
   const float* inv_a; const float* inv_b;
   double* row_part;     // [chunk][4][ldI]
 };
@@ -498,6 +508,11 @@ rowsum_tc_kernel(const __grid_constant__ CUtensorMap map_genes, const __grid_con
       int gt, ct0, nct;
       unit_info(unit, gt, ct0, nct);
       double s64 = 0.0;
+      float lsc = 1.0f;
+      if (CLAMP && p.lane_scale) {
+        const int64_t lr = (int64_t)gt * RT_TILE + row;
+        lsc = lr < p.ldI ? __ldg(p.lane_scale + lr) : 0.0f;
+      }
       for (int c = 0; c < nct; ++c) {
         const float* gp = p.g_col + (int64_t)(ct0 + c) * RT_TILE + ch * 32;
         tc::mbar_wait(&d_full[db], dph[db]);
@@ -519,7 +534,7 @@ rowsum_tc_kernel(const __grid_constant__ CUtensorMap map_genes, const __grid_con
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
             float xs = __uint_as_float(xr[k]);
-            if (CLAMP) xs = fminf(fmaxf(xs, -clampv), clampv);
+            if (CLAMP) xs = fminf(fmaxf(xs * lsc, -clampv), clampv);
             ts = fmaf(ex2_approx(fmaf(xs, L_lo, xs * L_hi)), gj[k], ts);
           }
         }
@@ -544,7 +559,7 @@ rowsum_tc_kernel(const __grid_constant__ CUtensorMap map_genes, const __grid_con
 // ---------------------------------------------------------------------------------
 bool eta_tc_supported(const PassGeom& g, const XDesc& x, int y_storage) {
   static const bool off = getenv("SCGBM_ETA_FFMA") != nullptr;
-  if (off || g.nbatch != 1 || x.M < 1 || x.M > 64 || !x.A16 || !x.B16) return false;
+  if (off || x.M < 1 || x.M > 64 || !x.A16 || !x.B16) return false;
   if (y_storage >= 0 && y_storage != SCGBM_STORE_U8 && y_storage != SCGBM_STORE_U16) return false;
   return true;
 }
@@ -574,6 +589,7 @@ void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const
   p.f_row = f_row; p.g_col = g_col; p.la_row = la_row; p.lb_col = lb_col;
   p.inv_a = fa.meta.get() + 1; p.inv_b = fb.meta.get() + 1;
   p.maxY = maxY; p.log_maxY = logf(maxY); p.rscale = resid.scale;
+  p.batch = g.batch; p.rowscale = x.rowscale;
   const int grid = std::min(p.n_units, ctx.num_sms);
   if (ws.scal_part.n < (int64_t)grid * 4) ws.scal_part.alloc((int64_t)grid * 4);
   p.scal_part = ws.scal_part.get();
@@ -585,20 +601,28 @@ void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const
   const CUtensorMap ml = make_tmap_2d(resid.lo, 2, false, (uint64_t)g.ldI, (uint64_t)g.J, (uint64_t)g.ldI * 2, FT_GENES, FT_CELLS, 128);
   {
     ProfScope ps(ctx.prof, SCGBM_K_FUSED, 1);
-#define LAUNCH_FUSED(YT, CL)                                                                                          \
-  do {                                                                                                                \
-    SCGBM_CUDA(cudaFuncSetAttribute(fused_tc_kernel<YT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
-    fused_tc_kernel<YT, CL><<<grid, FT_NT, smem_bytes, ctx.stream>>>(mc, mg, my, mh, ml, p);                            \
+#define LAUNCH_FUSED(YT, CL, MBF)                                                                                          \
+  do {                                                                                                                     \
+    SCGBM_CUDA(cudaFuncSetAttribute(fused_tc_kernel<YT, CL, MBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
+    fused_tc_kernel<YT, CL, MBF><<<grid, FT_NT, smem_bytes, ctx.stream>>>(mc, mg, my, mh, ml, p);                            \
   } while (0)
-    if (ybytes == 2) { if (x.clamp) LAUNCH_FUSED(uint16_t, true); else LAUNCH_FUSED(uint16_t, false); }
-    else { if (x.clamp) LAUNCH_FUSED(uint8_t, true); else LAUNCH_FUSED(uint8_t, false); }
+#define LAUNCH_FUSED_Y(YT)                                                                     \
+  do {                                                                                         \
+    if (mb) { if (x.clamp) LAUNCH_FUSED(YT, true, true); else LAUNCH_FUSED(YT, false, true); } \
+    else { if (x.clamp) LAUNCH_FUSED(YT, true, false); else LAUNCH_FUSED(YT, false, false); }  \
+  } while (0)
+    const bool mb = g.nbatch > 1;
+    if (ybytes == 2) LAUNCH_FUSED_Y(uint16_t); else LAUNCH_FUSED_Y(uint8_t);
+#undef LAUNCH_FUSED_Y
 #undef LAUNCH_FUSED
     SCGBM_LAUNCH_CHECK();
   }
   {
     ProfScope ps(ctx.prof, SCGBM_K_MISC, 2);
     scal_reduce_launch(ctx, grid, ws.scal_part.get(), out3);
-    ll_const_kernel<<<1, 1024, 0, ctx.stream>>>(g.I, alpha, rowsum_local, g.J, beta, y.colsum.get(), out3);
+    // alpha and the local row sums are ldI x nbatch with zero pad rows: one flat dot product
+    ll_const_kernel<<<1, 1024, 0, ctx.stream>>>(g.nbatch > 1 ? g.ldI * g.nbatch : g.I, alpha, rowsum_local, g.J, beta,
+                                                y.colsum.get(), out3);
     SCGBM_LAUNCH_CHECK();
   }
 }
@@ -607,7 +631,8 @@ void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const
 // `streamed` (TMEM columns).  rowsum: lanes = genes, streamed = cells, colfac = exp(beta);
 // colsum: lanes = cells, streamed = genes, colfac = exp(alpha).  colfac is zero padded to whole tiles.
 static void lane_sums_tc(Ctx& ctx, EtaWs& ws, const Factor16& lanes, const Factor16& streamed, int64_t ld_lanes,
-                         int64_t n_streamed, const float* colfac, bool clamp, double* out, int prof_class) {
+                         int64_t n_streamed, const float* colfac, bool clamp, double* out, int prof_class,
+                         const float* lane_scale = nullptr) {
   RowsumTcParams p;
   memset(&p, 0, sizeof(p));
   p.J = n_streamed; p.ldI = ld_lanes;
@@ -617,7 +642,7 @@ static void lane_sums_tc(Ctx& ctx, EtaWs& ws, const Factor16& lanes, const Facto
   int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div((int64_t)ctx.num_sms * 8, p.n_gene_tiles), ceil_div(p.n_cell_tiles, 4)));
   p.cell_tiles_per_chunk = (int)ceil_div(p.n_cell_tiles, chunks);
   p.n_chunks = (int)ceil_div(p.n_cell_tiles, p.cell_tiles_per_chunk);
-  p.g_col = colfac;
+  p.g_col = colfac; p.lane_scale = lane_scale;
   p.inv_a = lanes.meta.get() + 1; p.inv_b = streamed.meta.get() + 1;
   const int64_t n = ld_lanes;
   if (ws.row_part.n < (int64_t)p.n_chunks * 4 * n) ws.row_part.alloc((int64_t)p.n_chunks * 4 * n);
@@ -641,8 +666,30 @@ static void lane_sums_tc(Ctx& ctx, EtaWs& ws, const Factor16& lanes, const Facto
   rowpart_reduce_launch(ctx, p.n_chunks * 4, n, ws.row_part.get(), out);
 }
 
+__global__ void mask_batch_kernel(int64_t J, int64_t n_pad, const float* __restrict__ g, const int32_t* __restrict__ batch,
+                                  int k, float* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n_pad) out[j] = (j < J && batch[j] == k) ? g[j] : 0.0f;
+}
+
 void pass_rowsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* g_col, double* S) {
-  lane_sums_tc(ctx, ws, *x.A16, *x.B16, g.ldI, g.J, g_col, x.clamp != 0, S, SCGBM_K_ROWSUM);
+  if (g.nbatch == 1) {
+    lane_sums_tc(ctx, ws, *x.A16, *x.B16, g.ldI, g.J, g_col, x.clamp != 0, S, SCGBM_K_ROWSUM);
+    return;
+  }
+  // S_ik = sum over the cells of batch k: one pass per batch with exp(beta) masked to that batch
+  // (and, for the X0 form, the batch's row scaling as a per-lane factor)
+  const int64_t n_pad = g.ldJ + 128;
+  if (ws.gmask.n < n_pad) ws.gmask.alloc(n_pad);
+  for (int k = 0; k < g.nbatch; ++k) {
+    {
+      ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
+      mask_batch_kernel<<<(unsigned)ceil_div(n_pad, 256), 256, 0, ctx.stream>>>(g.J, n_pad, g_col, g.batch, k, ws.gmask.get());
+      SCGBM_LAUNCH_CHECK();
+    }
+    lane_sums_tc(ctx, ws, *x.A16, *x.B16, g.ldI, g.J, ws.gmask.get(), x.clamp != 0, S + (int64_t)k * g.ldI, SCGBM_K_ROWSUM,
+                 x.rowscale ? x.rowscale + (int64_t)k * g.ldI : nullptr);
+  }
 }
 
 // C_j = sum_i f_i exp(x_ij)   (R/fit.R:134): the same kernel with the roles of the factors swapped

@@ -244,7 +244,7 @@ struct FitState {
     stage_factor_kernel<<<GRID1(ldJ * f.M)>>>(J, ldJ, f.M, f.V.get(), nullptr, cs, f.B32.get());
     SCGBM_LAUNCH_CHECK();
     f.has16 = false;
-    if (nbatch == 1 && f.M <= 64) {
+    if (f.M <= 64) {
       stage_factor16(ctx, f.a16, I, ldI, f.M, 0, f.U.get(), f.d.get(), rs);
       stage_factor16(ctx, f.b16, J, ldJ, f.M, 1, f.V.get(), nullptr, cs);
       f.has16 = true;
@@ -461,7 +461,7 @@ struct FitRun {
     }
     st.stage_rows();
     if (a.infer_beta) {                                  // R/fit.R:133-135
-      if (tc_eta) pass_colsum_tc(ctx, st.eta, st.geom, xc, st.f_row.get(), st.Ccol.get());
+      if (tc_eta && nbatch == 1) pass_colsum_tc(ctx, st.eta, st.geom, xc, st.f_row.get(), st.Ccol.get());
       else pass_colsum(ctx, st.eta, st.geom, xc, st.f_row.get(), st.Ccol.get());
       ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
       beta_infer_kernel<<<GRID1(J)>>>(J, st.logcs.get(), st.Ccol.get(), st.beta.get());
