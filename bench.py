@@ -331,11 +331,27 @@ def main():
         barrier()
         prof = out["_prof"]
         n_it = out["_n_iter"]
+        # size-independent properties of the full-size fit (SURVEY section 4 iii), this rank's shard
+        acc_obj = np.asarray(out["obj"])
+        Uo, Vo = out["U"], out["V"]
+        vtv = Vo.T @ Vo
+        if dist is not None:
+            import torch
+            t = torch.from_numpy(np.ascontiguousarray(vtv)); dist.all_reduce(t); vtv = t.numpy()
+        checks = {
+            "obj_nondecreasing_from_3rd": bool(np.all(np.diff(acc_obj[2:]) >= -1e-9 * np.abs(acc_obj[2:-1]))) if len(acc_obj) > 3 else True,
+            "mean_alpha_abs": float(abs(out["alpha"].mean())),
+            "UtU_minus_I_max": float(np.abs(Uo.T @ Uo - np.eye(M)).max()),
+            "VtV_minus_I_max": float(np.abs(vtv - np.eye(M)).max()),
+            "D_descending": bool(np.all(np.diff(out["D"]) <= 0)),
+            "U_first_row_nonneg": bool(np.all(Uo[0] >= 0)),
+            "scores_eq_V_D_max": float(np.abs(out["scores"] - Vo * out["D"][None, :]).max()),
+        }
         e2e = {"value": n_it / wall, "unit": "iters/s", "h2d_bytes_per_step": prof["h2d_bytes"] / n_it,
                "d2h_bytes_per_step": prof["d2h_bytes"] / n_it, "fit_seconds": wall, "iterations": n_it,
                "accepted": int(len(out["obj"])), "device_ms": prof["total_ms"], "host_dtype": "int32",
                "pinned": bool(pinned), "objective_first_last": [float(out["obj"][0]), float(out["obj"][-1])],
-               "kernel_ms": {k: round(v, 1) for k, v in prof["ms"].items()},
+               "kernel_ms": {k: round(v, 1) for k, v in prof["ms"].items()}, "checks": checks,
                "call": f"gbm_sc(Y, M={M}, max_iter={args.e2e_max_iter}, return_W=False) with reference defaults tol=1e-4, min_iter=30"}
         del Yh
         if pinned:
