@@ -227,11 +227,20 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
     // parity-neutral (objective, alpha, angles unchanged to the digits printed), unlike hi-only Q1.
     static const bool env_start_full = getenv("SCGBM_START_FULL") != nullptr;
     ws.start_hi = was_warm && !env_start_full;
+    static const bool env_ustart = getenv("SCGBM_USTART") ? atoi(getenv("SCGBM_USTART")) != 0 : true;
+    const bool ustart = env_ustart && was_warm && ws.warm_calls >= 1;
     for (int cycle = 0; !restart; ++cycle) {
       ws.T.zero(ctx.stream);
-      op_mul(ctx, ws, op, V0, ldJ, b, ws.Qb.get(), o.variant, true);
-      ++passes;
-      sym_orth(ctx, ws.small, ldI, b, ws.Qb.get(), ldI, nullptr, ldI, 0, ws.tmpI.get(), robust, ws.flag.get());
+      if (ustart && cycle == 0) {
+        // Start the Krylov space from the previous call's left Ritz block (orthonormal already) instead
+        // of orth(G V_prev): one pass over the residual less.  Every later product uses the exact
+        // operator and the Ritz estimate decides whether the space is deep enough, exactly as before.
+        copy_mat(ctx, ldI, b, ws.Ub.get(), ldI, ws.Qb.get(), ldI);
+      } else {
+        op_mul(ctx, ws, op, V0, ldJ, b, ws.Qb.get(), o.variant, true);
+        ++passes;
+        sym_orth(ctx, ws.small, ldI, b, ws.Qb.get(), ldI, nullptr, ldI, 0, ws.tmpI.get(), robust, ws.flag.get());
+      }
       for (int t = 0;; ++t) {
         p = b * (t + 1);
         double* Zt = ws.Zb.get() + (int64_t)t * b * ldJ;
@@ -301,6 +310,7 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
     robust = true;
     ws.robust = true;   // the operator family of this fit is rank deficient: stay robust
   }
+  ws.warm_calls = was_warm ? ws.warm_calls + 1 : 0;
   ws.warm = true;
   ws.lowprec = false;
   if (fast_call) ++ws.fast_streak;

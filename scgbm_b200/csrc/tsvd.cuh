@@ -52,6 +52,7 @@ struct TsvdWs {
   int64_t passes_total = 0, calls = 0;
   double last_est = 1e300;  // residual estimate of the last call that ran a Krylov extension
   int fast_streak = 0;      // consecutive calls that skipped the extension
+  int warm_calls = 0;       // consecutive warm calls so far (Ub then belongs to the same operator family)
   bool lowprec = false;     // cold start, early cycles: products read only the residual's hi plane
   bool start_hi = false;    // warm call: the start block Q0 = orth(G V0) is built from the hi plane only
 };
