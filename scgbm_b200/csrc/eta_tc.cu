@@ -82,7 +82,7 @@ void stage_factor16(Ctx& ctx, Factor16& f, int64_t n_real, int64_t ld, int M, in
 }
 
 // ---------------------------------------------------------------------------------
-constexpr int FT_NT = 320;            // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int FT_NT = 352;            // warp 0 TMA loads, warp 1 MMA, warps 2-9 epilogue, warp 10 TMA stores
 constexpr int FT_EPI = 256;
 constexpr int FT_CELLS = 128;         // MMA M  (TMEM lanes = cells)
 constexpr int FT_GENES = 64;          // MMA N  (TMEM columns = genes)
@@ -121,7 +121,8 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
   uint64_t* d_full = bars + 6;    uint64_t* d_empty = bars + 8;   // [2]
   uint64_t* y_full = bars + 10;   uint64_t* y_empty = bars + 14;  // [<=4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-  double* red = reinterpret_cast<double*>(bars + 20);             // [8][4]
+  uint64_t* r_full = bars + 20;   uint64_t* r_free = bars + 22;   // [2] residual tile buffers: epilogue <-> store warp
+  double* red = reinterpret_cast<double*>(bars + 24);             // [8][4]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -131,6 +132,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1);
       tc::mbar_init(&d_full[s], 1); tc::mbar_init(&d_empty[s], FT_EPI);
+      tc::mbar_init(&r_full[s], 8); tc::mbar_init(&r_free[s], 1);
     }
     for (int s = 0; s < 4; ++s) { tc::mbar_init(&y_full[s], 1); tc::mbar_init(&y_empty[s], FT_EPI); }
     tc::fence_barrier_init();
@@ -204,6 +206,29 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
         }
       }
     }
+  } else if (warp == 10) {
+    if (lane == 0) {
+      // ===== TMA store warp: ships each finished residual tile; no CTA-wide barrier on this path =====
+      uint32_t rb = 0, ntile = 0;
+      uint32_t fph[2] = {0, 0};
+      for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+        int ct, gt0, ngt;
+        unit_info(unit, ct, gt0, ngt);
+        for (int g = 0; g < ngt; ++g, ++ntile) {
+          const int gene0 = (gt0 + g) * FT_GENES;
+          tc::mbar_wait_relaxed(&r_full[rb], fph[rb]);     // all 8 epilogue warps wrote (and proxy-fenced) their part
+          fph[rb] ^= 1;
+          uint8_t* rt = r_buf + rb * FT_R_BYTES;
+          tc::tma_store_2d(&map_hi, rt, gene0, ct * FT_CELLS);
+          tc::tma_store_2d(&map_lo, rt + FT_CELLS * 128, gene0, ct * FT_CELLS);
+          tc::tma_store_commit();
+          tc::tma_store_wait_read<1>();                    // the previous tile's store has drained the other buffer
+          if (ntile >= 1) tc::mbar_arrive(&r_free[rb ^ 1]);
+          rb ^= 1;
+        }
+      }
+      tc::tma_store_wait<0>();
+    }
   } else {
     // ===== epilogue: one cell per thread, 2 chunks of 16 genes per tile =====
     const int e = warp - 2;                 // 0..7
@@ -224,7 +249,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
     double sw64 = 0.0, syl64 = 0.0;
     float mw = 0.0f;
     uint32_t ys = 0, yph = 0, db = 0, rb = 0;
-    uint32_t dph[2] = {0, 0};
+    uint32_t dph[2] = {0, 0}, rfph[2] = {0, 0};
     for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
       int ct, gt0, ngt;
       unit_info(unit, ct, gt0, ngt);
@@ -240,9 +265,6 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
         dph[db] ^= 1;
         tc::mbar_wait(&y_full[ys], yph);
         tc::fence_after_sync();
-        // the store that read r_buf[rb] two tiles ago must have drained it
-        if (et == 0) tc::tma_store_wait_read<1>();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
         const uint8_t* yt = y_buf + ys * p.y_stage_bytes;
         uint8_t* rt = r_buf + rb * FT_R_BYTES;
         // issue every load of the tile's two chunks first (TMEM, Y from smem, f_i broadcast), wait once,
@@ -335,6 +357,10 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
             hp[k] = *reinterpret_cast<const uint32_t*>(&h2);
             lp[k] = *reinterpret_cast<const uint32_t*>(&l2);
           }
+          if (c == 0) {   // the store that read r_buf[rb] two tiles ago must have drained it
+            tc::mbar_wait(&r_free[rb], rfph[rb] ^ 1);
+            rfph[rb] ^= 1;
+          }
           const int q0 = col >> 3;
           uint8_t* rh = rt + row * 128;
           uint8_t* rl = rt + FT_CELLS * 128 + row * 128;
@@ -345,19 +371,14 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
         }
         // the Y stage is free again
         tc::mbar_arrive(&y_empty[ys]);
-        // hand the tile to the TMA store
+        // hand this warp's part of the tile to the store warp (generic-proxy writes -> async proxy)
         tc::fence_proxy_async();
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        if (et == 0) {
-          tc::tma_store_2d(&map_hi, rt, gene0, ct * FT_CELLS);
-          tc::tma_store_2d(&map_lo, rt + FT_CELLS * 128, gene0, ct * FT_CELLS);
-          tc::tma_store_commit();
-        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&r_full[rb]);
         db ^= 1; rb ^= 1;
         if (++ys == (uint32_t)p.y_stages) { ys = 0; yph ^= 1; }
       }
     }
-    if (et == 0) tc::tma_store_wait<0>();
     // CTA partial of the three scalars (fixed order)
     sw64 = warp_sum(sw64) * (double)inv_rs; syl64 = warp_sum(syl64); mw = warp_max(mw) * inv_rs;
     if (lane == 0) { red[e * 4 + 0] = sw64; red[e * 4 + 1] = syl64; red[e * 4 + 2] = (double)mw; }
@@ -582,7 +603,7 @@ void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const
   p.n_units = p.n_cell_tiles * chunks;
   const int ybytes = y.elem_bytes();
   p.y_stage_bytes = FT_CELLS * FT_GENES * ybytes;
-  const int fixed = p.nslab * FT_SLAB_A + 2 * p.nslab * FT_SLAB_B + 2 * FT_R_BYTES + 1024 + 512;
+  const int fixed = p.nslab * FT_SLAB_A + 2 * p.nslab * FT_SLAB_B + 2 * FT_R_BYTES + 1024 + 512;   // 512: barriers + CTA reduction scratch
   p.y_stages = std::min(4, (int)((225 * 1024 - fixed) / p.y_stage_bytes));
   SCGBM_REQUIRE(p.y_stages >= 2, "fused_tc: not enough shared memory for this M");
   const int smem_bytes = fixed + p.y_stages * p.y_stage_bytes;
