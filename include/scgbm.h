@@ -141,6 +141,13 @@ typedef struct scgbm_fit_out {
   int32_t y_storage;    /* format actually used                                              */
   double  max_Y;
   scgbm_profile prof;
+  /* extension: the factors of the X that alpha, beta and W belong to (the REVERTED X on a
+   * convergence break, quirk Q6), so that get.se can re-evaluate W on the device when return.W = FALSE.
+   * Caller-allocated or NULL.  x_rank = M (Xu = u diag(d), Xv = v), 0 (X = 0), or -1 when X is still the
+   * clamped initial point of R/fit.R:116-120, which has no factor form (then Xu/Xv are not written). */
+  double* Xu;     /* I x M */
+  double* Xv;     /* J x M */
+  int32_t x_rank;
 } scgbm_fit_out;
 
 int scgbm_fit(const scgbm_fit_args* args, scgbm_fit_out* out);

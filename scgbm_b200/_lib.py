@@ -61,7 +61,8 @@ class FitOut(C.Structure):
                 ("obj", C.c_void_p), ("time", C.c_void_p), ("W", C.c_void_p),
                 ("LL", C.c_void_p), ("accepted", C.c_void_p),
                 ("n_obj", C.c_int32), ("n_iter", C.c_int32), ("hit_max_iter", C.c_int32),
-                ("y_storage", C.c_int32), ("max_Y", C.c_double), ("prof", Profile)]
+                ("y_storage", C.c_int32), ("max_Y", C.c_double), ("prof", Profile),
+                ("Xu", C.c_void_p), ("Xv", C.c_void_p), ("x_rank", C.c_int32)]
 
 
 class SeArgs(C.Structure):

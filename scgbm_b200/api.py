@@ -66,14 +66,17 @@ def _batch_codes(batch, J):
 def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False, return_W=True,
            batch=None, time_by_iter=False, min_iter=30, *, device=-1, comm=None, y_storage=L.STORE_AUTO,
            svd_extra=0, svd_depth=0, svd_tol=0.0, seed=0, profile=False, verbose=False, quiet=True,
-           diagnostics=False, y_device_ptr=None, y_device_shape=None, y_device_dtype=None, rng=None):
+           diagnostics=False, y_device_ptr=None, y_device_shape=None, y_device_dtype=None, rng=None,
+           keep_factors=False):
     """gbm.sc(Y, M, max.iter, tol, subset, ncores, infer.beta, return.W, batch,
     time.by.iter, min.iter)   -- R/fit.R:52-62.
 
     Extensions (keyword only): `device`, `comm` (one NCCL rank per GPU; Y then holds
     this rank's cells), `y_storage`, `svd_*`, `seed`, `profile`, `diagnostics`
     (adds `_LL`, `_accepted`, `_n_iter`, `_prof`), `y_device_ptr` (Y already
-    resident in HBM in the library's own layout).
+    resident in HBM in the library's own layout), `keep_factors` (adds `_Xu`, `_Xv`,
+    `_batch`: the factors of the X that alpha/beta/W belong to, so that `get_se` works
+    after `return_W=False` -- the reference cannot, quirk Q9).
     """
     if subset is not None:                                     # R/fit.R:67-73
         from .projection import gbm_proj_parallel
@@ -137,6 +140,9 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
     o.U = L.ptr(U); o.D = L.ptr(D); o.V = L.ptr(V); o.loadings = L.ptr(loadings); o.scores = L.ptr(scores)
     o.alpha = L.ptr(alpha); o.beta = L.ptr(beta); o.obj = L.ptr(obj); o.time = L.ptr(tvec)
     o.W = L.ptr(W); o.LL = L.ptr(LLv); o.accepted = L.ptr(acc)
+    Xu = np.zeros((I, M), order="F") if keep_factors else None
+    Xv = np.zeros((J, M), order="F") if keep_factors else None
+    o.Xu = L.ptr(Xu); o.Xv = L.ptr(Xv)
     st = lib.scgbm_fit(C.byref(a), C.byref(o))
     if st == 1:
         raise RError(st, (lib.scgbm_last_error() or b"").decode())
@@ -158,6 +164,9 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
     if not quiet:
         print("For users of newer versions (1.0.1+): the `scores` matrix now contains factor scores, "
               "the `V` matrix is UNSCALED scores.", file=sys.stderr)   # R/fit.R:209
+    if keep_factors:
+        out["_x_rank"] = int(o.x_rank)
+        out["_Xu"] = Xu; out["_Xv"] = Xv; out["_batch"] = codes
     if diagnostics or profile:
         out["_LL"] = LLv[: o.n_iter].copy()
         out["_accepted"] = acc[: o.n_iter].astype(bool)
@@ -169,21 +178,35 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
     return out
 
 
-def get_se(out, EPS=0.0, *, device=-1, profile=False):
+def get_se(out, EPS=0.0, *, device=-1, comm=None, profile=False):
     """get.se(out, EPS)  -- R/uncertainty.R:14-35.  Needs out['W'] like the reference
-    (quirk Q9)."""
+    (quirk Q9), or -- extension -- the `keep_factors=True` outputs of gbm_sc, from which W is
+    re-evaluated on the device chunk by chunk (the only option at sizes where W cannot exist)."""
     lib = L.load()
-    if "W" not in out or out["W"] is None:
-        raise RError(1, "get.se needs out$W: fit with return.W = TRUE (R/uncertainty.R:18)")
     U = np.asfortranarray(out["U"], dtype=np.float64)
     S = np.asfortranarray(out["scores"], dtype=np.float64)
-    W = np.asfortranarray(out["W"], dtype=np.float64)
-    I, J = W.shape
     M = len(out["D"])
-    se_s = np.zeros((J, M), order="F"); se_l = np.zeros((I, M), order="F")
     a = L.SeArgs()
-    a.I = I; a.J = J; a.M = M; a.U = L.ptr(U); a.scores = L.ptr(S); a.W = L.ptr(W)
-    a.EPS = float(EPS); a.device = int(device); a.nbatch = 1; a.profile = int(bool(profile))
+    keep = []
+    if out.get("W") is not None:
+        W = np.asfortranarray(out["W"], dtype=np.float64)
+        I, J = W.shape
+        a.W = L.ptr(W); a.nbatch = 1
+    elif out.get("_Xu") is not None and out.get("_x_rank", -1) >= 0:
+        I, J = U.shape[0], S.shape[0]
+        al = np.asfortranarray(out["alpha"], dtype=np.float64).reshape(I, -1, order="F")
+        be = np.ascontiguousarray(out["beta"], dtype=np.float64)
+        Xu = np.asfortranarray(out["_Xu"], dtype=np.float64); Xv = np.asfortranarray(out["_Xv"], dtype=np.float64)
+        bt = None if out.get("_batch") is None else np.ascontiguousarray(out["_batch"], dtype=np.int32)   # 1-based, R/fit.R:90
+        keep = [al, be, Xu, Xv, bt]
+        a.W = None; a.alpha = L.ptr(al); a.beta = L.ptr(be); a.batch = L.ptr(bt); a.nbatch = al.shape[1]
+        a.Xu = L.ptr(Xu); a.Xv = L.ptr(Xv); a.Mx = int(out["_x_rank"])
+    else:
+        raise RError(1, "get.se needs out$W: fit with return.W = TRUE (R/uncertainty.R:18) or keep_factors=True")
+    se_s = np.zeros((J, M), order="F"); se_l = np.zeros((I, M), order="F")
+    a.I = I; a.J = J; a.M = M; a.U = L.ptr(U); a.scores = L.ptr(S)
+    a.comm = comm.handle if comm is not None else None
+    a.EPS = float(EPS); a.device = int(device); a.profile = int(bool(profile))
     o = L.SeOut()
     o.se_scores = L.ptr(se_s); o.se_loadings = L.ptr(se_l)
     st = lib.scgbm_get_se(C.byref(a), C.byref(o))

@@ -623,6 +623,28 @@ struct FitRun {
       for (int64_t i2 = 0; i2 < I; ++i2) out->alpha[(size_t)k * I + i2] = hA[(size_t)k * ldI + i2];
     for (int64_t j2 = 0; j2 < J; ++j2) out->beta[j2] = hB[j2];
 
+    out->x_rank = -1;
+    {
+      const Factor& fx = st.slot[cur];
+      if (fx.kind == XK_ZERO) out->x_rank = 0;
+      else if (fx.kind == XK_LOWRANK) out->x_rank = fx.M;
+      if (out->Xu && out->Xv && out->x_rank >= 0) {
+        std::vector<double> xU((size_t)ldI * M), xV((size_t)ldJ * M), xD(M);
+        if (fx.kind == XK_LOWRANK) {
+          SCGBM_CUDA(cudaMemcpyAsync(xU.data(), fx.U.get(), xU.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+          SCGBM_CUDA(cudaMemcpyAsync(xV.data(), fx.V.get(), xV.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+          SCGBM_CUDA(cudaMemcpyAsync(xD.data(), fx.d.get(), M * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+          ctx.sync();
+          ctx.prof.d2h_bytes += (double)(xU.size() + xV.size()) * sizeof(double);
+        }
+        for (int m2 = 0; m2 < M; ++m2) {
+          for (int64_t i2 = 0; i2 < I; ++i2)
+            out->Xu[(size_t)m2 * I + i2] = fx.kind == XK_LOWRANK ? xU[(size_t)m2 * ldI + i2] * xD[m2] : 0.0;
+          for (int64_t j2 = 0; j2 < J; ++j2)
+            out->Xv[(size_t)m2 * J + j2] = fx.kind == XK_LOWRANK ? xV[(size_t)m2 * ldJ + j2] : 0.0;
+        }
+      }
+    }
     if (a.return_W && out->W) {                          // R/fit.R:189-191 (unclipped, current X)
       const Factor& fc = st.slot[cur];
       int64_t jc_max = std::max<int64_t>(1, (int64_t)(64ll << 20) / I);

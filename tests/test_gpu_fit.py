@@ -117,6 +117,31 @@ def test_storage_formats_agree(storage, dtype):
     assert out["_y_storage"] == (storage if storage else 2)
 
 
+def test_get_se_without_W():
+    """get.se after return.W = FALSE, W re-evaluated on the device from the kept factors
+    (Q6: the reverted X) -- same standard errors as from the returned W."""
+    from scgbm_b200 import gbm_sc, get_se
+    rng = np.random.default_rng(5)
+    Y = _sim(240, 610, 5, seed=31, nb=1.0)
+    full = gbm_sc(Y, 5, keep_factors=True)
+    assert full["_x_rank"] == 5
+    se_w = get_se(full)
+    lean = dict(full); lean["W"] = None
+    se_f = get_se(lean)
+    np.testing.assert_allclose(se_f["se_scores"], se_w["se_scores"], rtol=1e-9)
+    np.testing.assert_allclose(se_f["se_loadings"], se_w["se_loadings"], rtol=1e-9)
+    # with batches
+    labels = rng.integers(0, 2, size=Y.shape[1])
+    Yb = Y + 1 * (rng.random(Y.shape) < 0.2)
+    fb = gbm_sc(Yb, 4, batch=labels, max_iter=12, keep_factors=True)
+    lean = dict(fb); lean["W"] = None
+    np.testing.assert_allclose(get_se(lean)["se_scores"], get_se(fb)["se_scores"], rtol=1e-9)
+    # no W and no factors: the reference's own failure mode (Q9)
+    from scgbm_b200.api import RError
+    with pytest.raises(RError, match="needs out"):
+        get_se(gbm_sc(Y, 5, return_W=False, max_iter=5))
+
+
 def test_sparse_input_equals_dense():
     """dgCMatrix-style column-compressed input gives bit-identical sums to the dense path."""
     import scipy.sparse as sp
