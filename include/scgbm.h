@@ -208,6 +208,11 @@ typedef struct scgbm_proj_args {
   int32_t  glm_maxit;   /* fastglm default 100  */
   int32_t  device;
   int32_t  profile;
+  /* sparse input, used when Y == NULL (same meaning as in scgbm_fit_args): I_full x J dgCMatrix slots */
+  const int32_t* csc_i;
+  const int64_t* csc_p;
+  const void*    csc_x;
+  int32_t  csc_x_dtype;
 } scgbm_proj_args;
 
 typedef struct scgbm_proj_out {

@@ -83,7 +83,8 @@ class ProjArgs(C.Structure):
                 ("I_full", C.c_int64), ("J", C.c_int64), ("ldY", C.c_int64),
                 ("ixs", C.c_void_p), ("Ik", C.c_int64), ("M", C.c_int32),
                 ("U", C.c_void_p), ("alpha", C.c_void_p), ("glm_tol", C.c_double),
-                ("glm_maxit", C.c_int32), ("device", C.c_int32), ("profile", C.c_int32)]
+                ("glm_maxit", C.c_int32), ("device", C.c_int32), ("profile", C.c_int32),
+                ("csc_i", C.c_void_p), ("csc_p", C.c_void_p), ("csc_x", C.c_void_p), ("csc_x_dtype", C.c_int32)]
 
 
 class ProjOut(C.Structure):

@@ -193,7 +193,7 @@ static void launch_proj(Ctx& ctx, const ProjParams& q, int storage, unsigned gri
 }
 
 void project_impl(const scgbm_proj_args* a, scgbm_proj_out* out) {
-  SCGBM_REQUIRE(a && out && a->Y && a->ixs && a->U && a->alpha, "NULL args");
+  SCGBM_REQUIRE(a && out && (a->Y || (a->csc_i && a->csc_p && a->csc_x)) && a->ixs && a->U && a->alpha, "NULL args");
   SCGBM_REQUIRE(out->beta && out->scores && out->se_scores && out->fail, "output buffers missing");
   SCGBM_REQUIRE(a->Ik >= 1 && a->J >= 1 && a->M >= 1, "bad shape");
   Ctx ctx(a->device, nullptr);
@@ -206,7 +206,16 @@ void project_impl(const scgbm_proj_args* a, scgbm_proj_out* out) {
   const int PT = (int)ceil_div(T, WG_NT);
   SCGBM_REQUIRE(PT <= 9 && p <= WG_PMAX, "projection: M too large (M <= 63)");
   Counts Y;
-  load_counts_rows(ctx, a->Y, a->y_dtype, a->y_on_device, a->I_full, J, a->ldY, a->ixs, Ik, Y);   // Y[ixs,]  R/fit.R:237
+  if (a->Y) {
+    load_counts_rows(ctx, a->Y, a->y_dtype, a->y_on_device, a->I_full, J, a->ldY, a->ixs, Ik, Y);   // Y[ixs,]  R/fit.R:237
+  } else {
+    // sparse Y: densify all genes on the device first (scatter), then gather the kept rows from there
+    Counts full;
+    load_counts_csc(ctx, a->csc_i, a->csc_p, a->csc_x, a->csc_x_dtype, a->I_full, J, nullptr, 1, SCGBM_STORE_AUTO, full);
+    const int dt = full.storage == SCGBM_STORE_U8 ? SCGBM_U8 : (full.storage == SCGBM_STORE_U16 ? SCGBM_U16 : SCGBM_F32);
+    load_counts_rows(ctx, full.data, dt, 1, a->I_full, J, full.ld, a->ixs, Ik, Y);
+    ctx.sync();
+  }
   DevBuf<double> U(Ik * M), X(Ik * p), off(Ik), coef(J * p), se(J * p);
   DevBuf<int8_t> fail(J);
   DevBuf<int32_t> iters(J);

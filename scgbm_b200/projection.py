@@ -13,11 +13,17 @@ from . import _lib as L
 
 def gbm_proj_parallel(Y, M, subsample=2000, min_counts=5, ncores=1, tol=1e-4, max_iter=100, *,
                       device=-1, rng=None, profile=False, svd_tol=0.0, seed=0, glm_tol=1e-8, glm_maxit=100):
-    from .api import gbm_sc, _as_counts
+    from .api import gbm_sc, _as_counts, _is_sparse, _NP2DT
     lib = L.load()
-    Yh, y_dt = _as_counts(Y)
-    I, J = Yh.shape
-    rs = Yh.sum(axis=1, dtype=np.float64)
+    sparse = _is_sparse(Y)
+    if sparse:                       # dgCMatrix-style input stays sparse on the host (R/fit.R:224 densifies only Y.sub)
+        Ys = Y.tocsc()
+        I, J = Ys.shape
+        rs = np.asarray(Ys.sum(axis=1), dtype=np.float64).ravel()
+    else:
+        Yh, y_dt = _as_counts(Y)
+        I, J = Yh.shape
+        rs = Yh.sum(axis=1, dtype=np.float64)
     with np.errstate(divide="ignore"):
         alphas_full = np.log(rs)                                           # R/fit.R:217
     if np.ndim(subsample) == 0:                                            # R/fit.R:218-220
@@ -25,7 +31,7 @@ def gbm_proj_parallel(Y, M, subsample=2000, min_counts=5, ncores=1, tol=1e-4, ma
         jxs = rng.choice(J, size=int(subsample), replace=False)            # sample(1:J, size)
     else:
         jxs = np.asarray(subsample, dtype=np.int64) - 1                    # 1-based like R (:221-223)
-    Y_sub = np.asfortranarray(Yh[:, jxs])                                  # as.matrix(Y.sub)  :224
+    Y_sub = np.asfortranarray(Ys[:, jxs].toarray() if sparse else Yh[:, jxs])   # as.matrix(Y.sub)  :224
     ixs = np.nonzero(Y_sub.sum(axis=1, dtype=np.float64) > 5)[0]           # hard-coded 5  :225
     Y_sub = np.asfortranarray(Y_sub[ixs, :])
     out = gbm_sc(Y_sub, M, tol=tol, max_iter=max_iter, device=device, profile=profile,
@@ -36,7 +42,15 @@ def gbm_proj_parallel(Y, M, subsample=2000, min_counts=5, ncores=1, tol=1e-4, ma
     beta = np.zeros(J); scores = np.zeros((J, M), order="F"); se_scores = np.zeros((J, M), order="F")
     fail = np.zeros(J, dtype=np.int8); iters = np.zeros(J, dtype=np.int32)
     a = L.ProjArgs()
-    a.Y = L.ptr(Yh); a.y_dtype = y_dt; a.y_on_device = 0; a.I_full = I; a.J = J; a.ldY = I
+    if sparse:
+        xs = np.ascontiguousarray(Ys.data)
+        if xs.dtype not in _NP2DT:
+            xs = xs.astype(np.float64)
+        ci = np.ascontiguousarray(Ys.indices, dtype=np.int32); cp = np.ascontiguousarray(Ys.indptr, dtype=np.int64)
+        a.Y = None; a.csc_i = L.ptr(ci); a.csc_p = L.ptr(cp); a.csc_x = L.ptr(xs); a.csc_x_dtype = _NP2DT[xs.dtype]
+        a.y_dtype = 0; a.y_on_device = 0; a.I_full = I; a.J = J; a.ldY = I
+    else:
+        a.Y = L.ptr(Yh); a.y_dtype = y_dt; a.y_on_device = 0; a.I_full = I; a.J = J; a.ldY = I
     a.ixs = L.ptr(ixs64); a.Ik = len(ixs64); a.M = int(M); a.U = L.ptr(Uk); a.alpha = L.ptr(alpha_k)
     a.glm_tol = float(glm_tol); a.glm_maxit = int(glm_maxit); a.device = int(device); a.profile = int(bool(profile))
     o = L.ProjOut()

@@ -249,6 +249,12 @@ def test_projection_matches_oracle():
     assert np.all(out["U"][np.setdiff1d(np.arange(Y.shape[0]), out["_ixs"])] == 0)
     # and the subsample fit itself is a parity-checked fit
     assert assert_fit_parity(o_gbm_sc(Ysub[ixs], 4), sub) in ("full", "knife-edge")
+    # sparse (dgCMatrix-style) input takes the same path after the on-device scatter
+    import scipy.sparse as sp
+    outs = gbm_sc(sp.csc_matrix(Y.astype(np.float64)), 4, subset=idx)
+    np.testing.assert_allclose(outs["scores"], out["scores"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(outs["se_scores"], out["se_scores"], rtol=1e-12)
+    np.testing.assert_allclose(outs["alpha"], out["alpha"], rtol=0, atol=1e-12)
 
 
 def test_projection_glm_kernel_exact():
