@@ -82,7 +82,8 @@ void stage_factor16(Ctx& ctx, Factor16& f, int64_t n_real, int64_t ld, int M, in
 }
 
 // ---------------------------------------------------------------------------------
-constexpr int FT_NT = 352;            // warp 0 TMA loads, warp 1 MMA, warps 2-9 epilogue, warp 10 TMA stores
+constexpr int FT_NT = 384;            // warp 0 TMA factor loads, 1 MMA, 2-9 epilogue, 10 TMA stores, 11 TMA Y loads
+constexpr int FT_NB = 3;              // gene-operand ring depth
 constexpr int FT_EPI = 256;
 constexpr int FT_CELLS = 128;         // MMA M  (TMEM lanes = cells)
 constexpr int FT_GENES = 64;          // MMA N  (TMEM columns = genes)
@@ -112,25 +113,26 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_buf = smem;                                          // nslab * 16 KB (cells)
-  uint8_t* b_buf = a_buf + p.nslab * FT_SLAB_A;                   // 2 * nslab * 8 KB (genes)
-  uint8_t* y_buf = b_buf + 2 * p.nslab * FT_SLAB_B;               // y_stages * y_stage_bytes
+  uint8_t* b_buf = a_buf + p.nslab * FT_SLAB_A;                   // FT_NB * nslab * 8 KB (genes)
+  uint8_t* y_buf = b_buf + FT_NB * p.nslab * FT_SLAB_B;           // y_stages * y_stage_bytes
   uint8_t* r_buf = y_buf + p.y_stages * p.y_stage_bytes;          // 2 * 32 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(r_buf + 2 * FT_R_BYTES);
   uint64_t* a_full = bars;        uint64_t* a_empty = bars + 1;
-  uint64_t* b_full = bars + 2;    uint64_t* b_empty = bars + 4;   // [2]
-  uint64_t* d_full = bars + 6;    uint64_t* d_empty = bars + 8;   // [2]
-  uint64_t* y_full = bars + 10;   uint64_t* y_empty = bars + 14;  // [<=4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* b_full = bars + 2;    uint64_t* b_empty = bars + 5;   // [FT_NB]
+  uint64_t* d_full = bars + 8;    uint64_t* d_empty = bars + 10;  // [2]
+  uint64_t* y_full = bars + 12;   uint64_t* y_empty = bars + 16;  // [<=4]
   uint64_t* r_full = bars + 20;   uint64_t* r_free = bars + 22;   // [2] residual tile buffers: epilogue <-> store warp
-  double* red = reinterpret_cast<double*>(bars + 24);             // [8][4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  double* red = reinterpret_cast<double*>(bars + 26);             // [8][4]
+  float* f_ring = reinterpret_cast<float*>(bars + 64);            // [<=4][64] exp(alpha_i) of the gene tile, with each Y stage
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&map_cells); tc::tma_prefetch_desc(&map_genes); tc::tma_prefetch_desc(&map_y);
     tc::tma_prefetch_desc(&map_hi); tc::tma_prefetch_desc(&map_lo);
     tc::mbar_init(a_full, 1); tc::mbar_init(a_empty, 1);
+    for (int s = 0; s < FT_NB; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1);
       tc::mbar_init(&d_full[s], 1); tc::mbar_init(&d_empty[s], FT_EPI);
       tc::mbar_init(&r_full[s], 8); tc::mbar_init(&r_free[s], 1);
     }
@@ -153,8 +155,8 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer =====
-      uint32_t bs = 0, bph = 0, ys = 0, yph = 0, aph = 0;
+      // ===== TMA producer of the factor operands (L2-resident) =====
+      uint32_t bs = 0, bph = 0, aph = 0;
       for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
         int ct, gt0, ngt;
         unit_info(unit, ct, gt0, ngt);
@@ -168,10 +170,26 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
           tc::mbar_arrive_expect_tx(&b_full[bs], p.nslab * FT_SLAB_B);
           for (int s = 0; s < p.nslab; ++s)
             tc::tma_load_2d(&map_genes, &b_full[bs], b_buf + (bs * p.nslab + s) * FT_SLAB_B, s * 64, gene0);
-          if (++bs == 2) { bs = 0; bph ^= 1; }
+          if (++bs == FT_NB) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 11) {
+    if (lane == 0) {
+      // ===== TMA producer of the count tiles (HBM): runs y_stages tiles ahead of the epilogue,
+      // independent of the MMA pipeline (ncu: the epilogue spent 10 % of its samples waiting for Y
+      // while these loads were queued behind the factor ring) =====
+      uint32_t ys = 0, yph = 0;
+      for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+        int ct, gt0, ngt;
+        unit_info(unit, ct, gt0, ngt);
+        for (int g = 0; g < ngt; ++g) {
           tc::mbar_wait_relaxed(&y_empty[ys], yph ^ 1);
-          tc::mbar_arrive_expect_tx(&y_full[ys], p.y_stage_bytes);
-          tc::tma_load_2d(&map_y, &y_full[ys], y_buf + ys * p.y_stage_bytes, gene0, ct * FT_CELLS);
+          // f_i rides along with the count tile (single batch): the 80 KB vector does not survive in the
+          // ~14 KB of L1 left beside 214 KB of shared memory, and an L2 round trip per chunk stalls the epilogue
+          tc::mbar_arrive_expect_tx(&y_full[ys], p.y_stage_bytes + (MB ? 0 : FT_GENES * 4));
+          tc::tma_load_2d(&map_y, &y_full[ys], y_buf + ys * p.y_stage_bytes, (gt0 + g) * FT_GENES, ct * FT_CELLS);
+          if (!MB) tc::bulk_load_1d(f_ring + ys * FT_GENES, p.f_row + (int64_t)(gt0 + g) * FT_GENES, FT_GENES * 4, &y_full[ys]);
           if (++ys == (uint32_t)p.y_stages) { ys = 0; yph ^= 1; }
         }
       }
@@ -202,7 +220,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
           tc::mma_commit(&d_full[db]);
           if (g == ngt - 1) tc::mma_commit(a_empty);
           dph[db] ^= 1; db ^= 1;
-          if (++bs == 2) { bs = 0; bph ^= 1; }
+          if (++bs == FT_NB) { bs = 0; bph ^= 1; }
         }
       }
     }
@@ -285,7 +303,9 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
             yv[c][1] = make_uint4(0u, 0u, 0u, 0u);
           }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) fv[c][k] = __ldg(reinterpret_cast<const float4*>(p.f_row + boff + gene0 + col) + k);
+          for (int k = 0; k < 4; ++k)
+            fv[c][k] = MB ? __ldg(reinterpret_cast<const float4*>(p.f_row + boff + gene0 + col) + k)
+                          : *reinterpret_cast<const float4*>(f_ring + ys * FT_GENES + col + 4 * k);
         }
         tc::tmem_wait_ld();
         tc::fence_before_sync();
@@ -596,14 +616,28 @@ void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const
   p.nslab = fa.Kp / 64; p.kk = 3 * fa.Mp / 16;
   p.n_cell_tiles = (int)ceil_div(g.J, FT_CELLS);
   p.n_gene_tiles = (int)ceil_div(g.ldI, FT_GENES);
-  // enough units for ~16 per SM, at least 8 gene tiles each
-  int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div((int64_t)ctx.num_sms * 16, p.n_cell_tiles), p.n_gene_tiles / 8));
+  // units = cell tiles x gene chunks: ~16+ per SM, at least 8 gene tiles each; among the admissible
+  // chunk counts take the one whose last wave is fullest (the units are equal-sized, so the tail of a
+  // static round-robin is the only imbalance: ncu showed 7 % of the samples idling at the kernel's end)
+  int chunks = 1;
+  {
+    const int cmin = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div((int64_t)ctx.num_sms * 16, p.n_cell_tiles), p.n_gene_tiles / 8));
+    const int cmax = (int)std::max<int64_t>(cmin, std::min<int64_t>(p.n_gene_tiles / 8, 3 * cmin + 4));
+    double best = -1.0;
+    for (int c = cmin; c <= cmax; ++c) {
+      const int per = (int)ceil_div(p.n_gene_tiles, c);
+      const int64_t units = (int64_t)p.n_cell_tiles * ceil_div(p.n_gene_tiles, per);
+      const double eff = (double)units / ((double)ctx.num_sms * (double)ceil_div(units, ctx.num_sms));
+      if (eff > best + 1e-9) { best = eff; chunks = c; }
+    }
+  }
+  if (getenv("SCGBM_FUSED_CHUNKS")) chunks = std::max(1, atoi(getenv("SCGBM_FUSED_CHUNKS")));   // experiments
   p.gene_tiles_per_unit = (int)ceil_div(p.n_gene_tiles, chunks);
   chunks = (int)ceil_div(p.n_gene_tiles, p.gene_tiles_per_unit);
   p.n_units = p.n_cell_tiles * chunks;
   const int ybytes = y.elem_bytes();
   p.y_stage_bytes = FT_CELLS * FT_GENES * ybytes;
-  const int fixed = p.nslab * FT_SLAB_A + 2 * p.nslab * FT_SLAB_B + 2 * FT_R_BYTES + 1024 + 512;   // 512: barriers + CTA reduction scratch
+  const int fixed = p.nslab * FT_SLAB_A + FT_NB * p.nslab * FT_SLAB_B + 2 * FT_R_BYTES + 1024 + 512 + 4 * FT_GENES * 4;   // 512: barriers + CTA reduction scratch
   p.y_stages = std::min(4, (int)((225 * 1024 - fixed) / p.y_stage_bytes));
   SCGBM_REQUIRE(p.y_stages >= 2, "fused_tc: not enough shared memory for this M");
   const int smem_bytes = fixed + p.y_stages * p.y_stage_bytes;
