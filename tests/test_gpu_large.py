@@ -1,0 +1,35 @@
+"""Size-independent properties at a size the oracle cannot reach (SURVEY section 4 iii), and run-to-run
+reproducibility.  20 000 genes x 40 000 cells generated on the device with the benchmark's recipe."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_counts(I, J, d):
+    import bench
+    from scgbm_b200 import _lib as L
+    lib = L.load()
+    wl = bench.Workload(I, J, d)
+    return wl.host_slice(lib, L, 0, J, 0)
+
+
+def test_large_fit_invariants_and_reproducibility():
+    from scgbm_b200 import gbm_sc
+    I, J, M = 20000, 40000, 20
+    Y = _device_counts(I, J, M)
+    assert Y.shape == (I, J) and (Y == 0).mean() > 0.8
+    a = gbm_sc(Y, M, max_iter=14, return_W=False, diagnostics=True)
+    b = gbm_sc(Y, M, max_iter=14, return_W=False, diagnostics=True)
+    # fixed-order reductions everywhere: two runs agree bit for bit
+    np.testing.assert_array_equal(a["_LL"], b["_LL"])
+    np.testing.assert_array_equal(a["U"], b["U"])
+    obj = a["obj"]
+    assert np.all(np.diff(obj[2:]) >= -1e-9 * np.abs(obj[2:-1]))          # accepted objectives never decrease
+    assert abs(a["alpha"].mean()) < 1e-12                                   # R/fit.R:132
+    assert np.abs(a["U"].T @ a["U"] - np.eye(M)).max() < 1e-10
+    assert np.abs(a["V"].T @ a["V"] - np.eye(M)).max() < 1e-10
+    assert np.all(np.diff(a["D"]) <= 0) and np.all(a["U"][0] >= 0)
+    np.testing.assert_allclose(a["scores"], a["V"] * a["D"][None, :], rtol=0, atol=0)
