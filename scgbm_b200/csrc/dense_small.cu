@@ -167,9 +167,60 @@ ts_mul_kernel(int64_t n, int p, int q, const double* __restrict__ A, int64_t lda
   }
 }
 
+// Tall-skinny variant (q <= 64, p <= 128, large n): one thread per row keeps its q outputs in
+// registers, S sits in shared memory (broadcast reads), every global access is a coalesced column
+// segment and all of a thread's loads are independent -- HBM-bound instead of latency-bound.
+template <int QMAX>
+__global__ void __launch_bounds__(128)
+ts_mul_rows(int64_t n, int p, int q, const double* __restrict__ A, int64_t lda, const double* __restrict__ S, int lds,
+            double* __restrict__ C, int64_t ldc, double alpha, double beta) {
+  extern __shared__ double tm_sm[];         // [p][QMAX]
+  for (int idx = threadIdx.x; idx < p * QMAX; idx += blockDim.x) {
+    const int k = idx / QMAX, c = idx % QMAX;
+    tm_sm[idx] = c < q ? S[(int64_t)c * lds + k] : 0.0;
+  }
+  __syncthreads();
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double acc[QMAX];
+#pragma unroll
+  for (int c = 0; c < QMAX; ++c) acc[c] = 0.0;
+#pragma unroll 4
+  for (int k = 0; k < p; ++k) {
+    const double a = A[(int64_t)k * lda + r];
+    const double* srow = tm_sm + k * QMAX;
+#pragma unroll
+    for (int c = 0; c < QMAX; ++c) acc[c] = fma(a, srow[c], acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < QMAX; ++c) {
+    if (c < q) {
+      double* dst = &C[(int64_t)c * ldc + r];
+      const double old = (beta == 0.0) ? 0.0 : beta * (*dst);
+      *dst = old + alpha * acc[c];
+    }
+  }
+}
+
 void ts_mul(Ctx& ctx, int64_t n, int p, int q, const double* A, int64_t lda, const double* S,
             int lds, double* C, int64_t ldc, double alpha, double beta) {
   if (n <= 0 || q <= 0) return;
+  static const bool no_rows = getenv("SCGBM_MUL_OLD") != nullptr;
+  if (!no_rows && q <= 64 && p <= 160 && n >= 65536) {
+    ProfScope ps(ctx.prof, SCGBM_K_SMALL, 1);
+    const unsigned grid = (unsigned)ceil_div(n, 128);
+    if (q <= 32) {
+      const size_t smem = (size_t)p * 32 * sizeof(double);
+      ts_mul_rows<32><<<grid, 128, smem, ctx.stream>>>(n, p, q, A, lda, S, lds, C, ldc, alpha, beta);
+    } else {
+      const size_t smem = (size_t)p * 64 * sizeof(double);
+      if (smem > 48 * 1024)
+        SCGBM_CUDA(cudaFuncSetAttribute(ts_mul_rows<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ts_mul_rows<64><<<grid, 128, smem, ctx.stream>>>(n, p, q, A, lda, S, lds, C, ldc, alpha, beta);
+    }
+    SCGBM_LAUNCH_CHECK();
+    return;
+  }
   ProfScope ps(ctx.prof, SCGBM_K_SMALL, 1);
   dim3 grid((unsigned)ceil_div(n, TM_ROWS), (unsigned)ceil_div(q, TM_COLS));
   ts_mul_kernel<<<grid, TM_NT, 0, ctx.stream>>>(n, p, q, A, lda, S, lds, C, ldc, alpha, beta);
