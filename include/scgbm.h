@@ -107,7 +107,8 @@ typedef struct scgbm_fit_args {
   int32_t  svd_depth;   /* max Krylov extensions per cycle (default 3)              */
   double   svd_tol;     /* Ritz residual estimate to stop at (default 1e-4)         */
   uint64_t seed;        /* start block of the initial SVD                           */
-  int32_t  profile;     /* 1: per-class CUDA-event timing into out->prof            */
+  int32_t  profile;     /* 1: per-class CUDA-event timing into out->prof; 2: only the */
+                        /* fused pass (K4) is bracketed by events (launch counts stay) */
   int32_t  verbose;
   scgbm_progress_cb progress; /* called once per accepted iteration (R/fit.R:175)   */
   void*    progress_user;
@@ -161,6 +162,7 @@ typedef struct scgbm_fit_handle scgbm_fit_handle;
 int scgbm_fit_begin(const scgbm_fit_args* args, scgbm_fit_handle** handle);
 int scgbm_fit_step(scgbm_fit_handle* handle, int32_t n_steps, int32_t* done);
 int scgbm_fit_profile(scgbm_fit_handle* handle, scgbm_profile* prof); /* cumulative so far */
+int scgbm_fit_set_profile(scgbm_fit_handle* handle, int32_t level);    /* 0 / 1 / 2 as scgbm_fit_args.profile */
 int scgbm_fit_end(scgbm_fit_handle* handle, scgbm_fit_out* out);
 
 /* ---- get.se(out, EPS)   R/uncertainty.R:14-35 --------------------------------- */

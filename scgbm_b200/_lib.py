@@ -140,7 +140,7 @@ class EvalOut(C.Structure):
 
 # every symbol include/scgbm.h declares
 EXPORTS = [
-    "scgbm_fit", "scgbm_fit_begin", "scgbm_fit_step", "scgbm_fit_profile", "scgbm_fit_end", "scgbm_get_se", "scgbm_project", "scgbm_sim_counts",
+    "scgbm_fit", "scgbm_fit_begin", "scgbm_fit_step", "scgbm_fit_profile", "scgbm_fit_set_profile", "scgbm_fit_end", "scgbm_get_se", "scgbm_project", "scgbm_sim_counts",
     "scgbm_dev_alloc", "scgbm_dev_free", "scgbm_memcpy_d2h", "scgbm_memcpy_h2d",
     "scgbm_host_alloc_pinned", "scgbm_host_free_pinned", "scgbm_flush_l2",
     "scgbm_comm_unique_id", "scgbm_comm_init_rank", "scgbm_comm_destroy", "scgbm_comm_allreduce_f64",
@@ -167,6 +167,7 @@ def load():
     lib.scgbm_fit_begin.argtypes = [C.POINTER(FitArgs), C.POINTER(C.c_void_p)]
     lib.scgbm_fit_step.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
     lib.scgbm_fit_profile.argtypes = [C.c_void_p, C.POINTER(Profile)]
+    lib.scgbm_fit_set_profile.argtypes = [C.c_void_p, C.c_int32]
     lib.scgbm_fit_end.argtypes = [C.c_void_p, C.POINTER(FitOut)]
     lib.scgbm_get_se.argtypes = [C.POINTER(SeArgs), C.POINTER(SeOut)]
     lib.scgbm_project.argtypes = [C.POINTER(ProjArgs), C.POINTER(ProjOut)]

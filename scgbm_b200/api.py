@@ -132,7 +132,7 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
     a.y_storage = int(y_storage); a.device = int(device)
     a.comm = comm.handle if comm is not None else None
     a.svd_extra = int(svd_extra); a.svd_depth = int(svd_depth); a.svd_tol = float(svd_tol)
-    a.seed = int(seed); a.profile = int(bool(profile)); a.verbose = int(bool(verbose))
+    a.seed = int(seed); a.profile = int(profile); a.verbose = int(bool(verbose))   # profile: 0 / 1 all classes / 2 fused pass only
     a.progress = cb; a.progress_user = None
     if csc is not None:
         a.csc_i = L.ptr(csc[0]); a.csc_p = L.ptr(csc[1]); a.csc_x = L.ptr(csc[2]); a.csc_x_dtype = y_dt

@@ -15,6 +15,7 @@ struct FitRun;
 FitRun* fit_begin_impl(const scgbm_fit_args* a);
 int fit_step_impl(FitRun* r, int n_steps);
 void fit_profile_impl(FitRun* r, scgbm_profile* p);
+void fit_set_profile_impl(FitRun* r, int level);
 void fit_end_impl(FitRun* r, scgbm_fit_out* out);
 void get_se_impl(const scgbm_se_args* a, scgbm_se_out* out);
 void project_impl(const scgbm_proj_args* a, scgbm_proj_out* out);
@@ -64,6 +65,9 @@ int scgbm_fit_step(scgbm_fit_handle* h, int32_t n_steps, int32_t* done) {
 }
 int scgbm_fit_profile(scgbm_fit_handle* h, scgbm_profile* prof) {
   return guarded([&] { fit_profile_impl(reinterpret_cast<FitRun*>(h), prof); });
+}
+int scgbm_fit_set_profile(scgbm_fit_handle* h, int32_t level) {
+  return guarded([&] { fit_set_profile_impl(reinterpret_cast<FitRun*>(h), level); });
 }
 int scgbm_fit_end(scgbm_fit_handle* h, scgbm_fit_out* out) {
   return guarded([&] { fit_end_impl(reinterpret_cast<FitRun*>(h), out); });

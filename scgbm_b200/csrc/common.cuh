@@ -102,6 +102,7 @@ struct PinnedBuf {
 // ---------------------------------------------------------------------------------
 struct Profiler {
   bool timing = false;
+  bool fused_only = false;   // profile level 2: CUDA events around the K4 launches only (the roofline kernel)
   cudaStream_t stream = nullptr;
   int64_t launches[SCGBM_K_NCLASS] = {0};
   double ms[SCGBM_K_NCLASS] = {0};
@@ -119,13 +120,13 @@ struct Profiler {
   // begin/end bracket `n` kernel launches of class `cls`
   cudaEvent_t begin(int cls, int n = 1) {
     launches[cls] += n;
-    if (!timing) return nullptr;
+    if (!timing || (fused_only && cls != SCGBM_K_FUSED)) return nullptr;
     cudaEvent_t a = get_event();
     SCGBM_CUDA(cudaEventRecord(a, stream));
     return a;
   }
   void end(int cls, cudaEvent_t a) {
-    if (!timing) return;
+    if (!timing || a == nullptr) return;
     cudaEvent_t b = get_event();
     SCGBM_CUDA(cudaEventRecord(b, stream));
     pending.push_back({cls, a, b});

@@ -410,6 +410,7 @@ struct FitRun {
   explicit FitRun(const scgbm_fit_args& args)
       : a(args), ctx(args.device, reinterpret_cast<Comm*>(args.comm)), st(ctx, a) {
     ctx.prof.timing = a.profile != 0;
+    ctx.prof.fused_only = a.profile == 2;
     SCGBM_CUDA(cudaEventCreate(&ev0));
     SCGBM_CUDA(cudaEventCreate(&ev1));
     SCGBM_CUDA(cudaEventRecord(ev0, ctx.stream));
@@ -691,6 +692,13 @@ void fit_profile_impl(FitRun* r, scgbm_profile* p) {
   SCGBM_REQUIRE(r && p, "NULL handle");
   SCGBM_CUDA(cudaSetDevice(r->ctx.device));
   r->fill_profile(p);
+}
+void fit_set_profile_impl(FitRun* r, int level) {
+  SCGBM_REQUIRE(r, "NULL handle");
+  SCGBM_CUDA(cudaSetDevice(r->ctx.device));
+  r->ctx.prof.resolve();
+  r->ctx.prof.timing = level != 0;
+  r->ctx.prof.fused_only = level == 2;
 }
 void fit_end_impl(FitRun* r, scgbm_fit_out* out) {
   SCGBM_REQUIRE(r, "NULL handle");
