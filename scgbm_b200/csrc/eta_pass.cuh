@@ -66,9 +66,19 @@ void pass_rowsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, cons
 void pass_colsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* f_row, double* C);
 // alpha/beta (fp64) and this rank's row sums of Y close the objective:
 //   sum_nz Y log W = sum Y x + sum_i alpha_i rs_i + sum_j beta_j cs_j   (+ clip correction)
+// Optional rider of the fused pass: out (J x b, column-major) = R^T Q0 for the residual this pass produces,
+// Q0 given as the two scaled fp16 planes prod_t would build ([hi 32 | lo 32][ldk]; products.cuh).
+struct FusedProd {
+  const uint16_t* op16; int64_t ldk;
+  const float* op_inv;        // device: 1 / operand scale
+  int b;                      // block columns, <= 32
+  double* out; int64_t ldo;
+};
+bool fused_prod_supported(Ctx& ctx, const PassGeom& g, const XDesc& x);
 void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const Counts& y, const float* f_row,
                    const float* g_col, const float* la_row, const float* lb_col, const double* alpha,
-                   const double* beta, const double* rowsum_local, float maxY, ResidBuf resid, double* out3);
+                   const double* beta, const double* rowsum_local, float maxY, ResidBuf resid, double* out3,
+                   const FusedProd* prod = nullptr);
 // fixed-order second stages shared by both implementations
 void scal_reduce_launch(Ctx& ctx, int64_t ncta, const double* part, double* out3);
 void rowpart_reduce_launch(Ctx& ctx, int nchunk, int64_t n, const double* part, double* S);

@@ -84,7 +84,10 @@ void stage_factor16(Ctx& ctx, Factor16& f, int64_t n_real, int64_t ld, int M, in
 }
 
 // ---------------------------------------------------------------------------------
-constexpr int FT_NT = 384;            // warp 0 TMA factor loads, 1 MMA, 2-9 epilogue, 10 TMA stores, 11 TMA Y loads
+constexpr int FT_NT = 384;            // warp 0 TMA factor loads, 1 eta MMA, 2 retire (TMA stores [+ fused product]), 3 TMA Y loads, 4-11 epilogue
+constexpr int FT_NT_PROD = 512;       // + warps 12-15: fp64 drain of the product accumulator
+constexpr int FT_W_RETIRE = 2, FT_W_Y = 3, FT_W_EPI0 = 4, FT_W_DRAIN0 = 12;
+constexpr int FT_OP_BYTES = 64 * 128; // fused product: one operand tile, [hi 32 | lo 32 block columns][64 genes] fp16
 constexpr int FT_NB = 3;              // gene-operand ring depth
 constexpr int FT_EPI = 256;
 constexpr int FT_CELLS = 128;         // MMA M  (TMEM lanes = cells)
@@ -105,47 +108,71 @@ struct FusedTcParams {
   const int32_t* batch;               // J zero-based batch codes (MB only)
   const float* rowscale;              // ldI x nbatch X0 row scaling (MB + CLAMP only) or null
   double* scal_part;                  // [cta][4]
+  // fused first Krylov pass (PROD): prod_out[j, k] = sum_i R[i, j] Q0[i, k] for this pass's residual
+  int prod_b;                         // block columns (<= 32)
+  double* prod_out; int64_t prod_ld;  // J x prod_b, column-major
+  const float* op_inv;                // device: 1 / operand scale
 };
 
-template <typename YT, bool CLAMP, bool MB>
-__global__ void __launch_bounds__(FT_NT, 1)
+// PROD: the tile that the epilogue just wrote to shared memory for the TMA store is, as it lies there
+// (128 cells x 64 genes, K-major, 128B swizzle), the A operand of prod_t's UMMA.  The retire warp
+// multiplies it with the matching 64-gene tile of the fp16-split start block Q0 (the previous SVD's left
+// Ritz block, known before this pass) into a second TMEM accumulator; every two tiles four drain warps
+// (12-15, one per TMEM lane quarter) fold that accumulator into fp64 registers (same 128-step drain as prod_tc_kernel).  The warm SVD's
+// first pass G^T Q0 then needs no pass over the planes at all.  Requires one unit per cell tile.
+template <typename YT, bool CLAMP, bool MB, bool PROD>
+__global__ void __launch_bounds__(PROD ? FT_NT_PROD : FT_NT, 1)
 fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_constant__ CUtensorMap map_genes,
                 const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_hi,
-                const __grid_constant__ CUtensorMap map_lo, const FusedTcParams p) {
+                const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_op,
+                const FusedTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_buf = smem;                                          // nslab * 16 KB (cells)
   uint8_t* b_buf = a_buf + p.nslab * FT_SLAB_A;                   // FT_NB * nslab * 8 KB (genes)
   uint8_t* y_buf = b_buf + FT_NB * p.nslab * FT_SLAB_B;           // y_stages * y_stage_bytes
   uint8_t* r_buf = y_buf + p.y_stages * p.y_stage_bytes;          // 2 * 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(r_buf + 2 * FT_R_BYTES);
+  uint8_t* op_buf = r_buf + 2 * FT_R_BYTES;                       // PROD: 2 * 8 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(op_buf + (PROD ? 2 * FT_OP_BYTES : 0));
   uint64_t* a_full = bars;        uint64_t* a_empty = bars + 1;
   uint64_t* b_full = bars + 2;    uint64_t* b_empty = bars + 5;   // [FT_NB]
   uint64_t* d_full = bars + 8;    uint64_t* d_empty = bars + 10;  // [2]
   uint64_t* y_full = bars + 12;   uint64_t* y_empty = bars + 16;  // [<=4]
   uint64_t* r_full = bars + 20;   uint64_t* r_free = bars + 22;   // [2] residual tile buffers: epilogue <-> store warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
-  double* red = reinterpret_cast<double*>(bars + 26);             // [8][4]
-  float* f_ring = reinterpret_cast<float*>(bars + 64);            // [<=4][64] exp(alpha_i) of the gene tile, with each Y stage
+  uint64_t* op_full = bars + 26;  uint64_t* op_empty = bars + 28; // [2] PROD: operand tiles, retire warp <-> tensor core
+  uint64_t* p_full = bars + 30;   uint64_t* p_empty = bars + 32;  // [2] PROD: product accumulators, tensor core <-> epilogue
+  double* red = reinterpret_cast<double*>(bars + 34);             // [8][4]
+  float* f_ring = reinterpret_cast<float*>(bars + 66);            // [<=4][64] exp(alpha_i) of the gene tile, with each Y stage
+  constexpr int TMEM_COLS = PROD ? 256 : 128;                     // eta x2 at 0/64; PROD: products x2 at 128/192
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&map_cells); tc::tma_prefetch_desc(&map_genes); tc::tma_prefetch_desc(&map_y);
     tc::tma_prefetch_desc(&map_hi); tc::tma_prefetch_desc(&map_lo);
+    if (PROD) tc::tma_prefetch_desc(&map_op);
     tc::mbar_init(a_full, 1); tc::mbar_init(a_empty, 1);
     for (int s = 0; s < FT_NB; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&d_full[s], 1); tc::mbar_init(&d_empty[s], FT_EPI);
-      tc::mbar_init(&r_full[s], 8); tc::mbar_init(&r_free[s], 1);
+      tc::mbar_init(&r_full[s], 8); tc::mbar_init(&r_free[s], PROD ? 2 : 1);   // PROD: store drained + product UMMAs done
+      tc::mbar_init(&op_full[s], 1); tc::mbar_init(&op_empty[s], 1);
+      tc::mbar_init(&p_full[s], 1); tc::mbar_init(&p_empty[s], 128);
     }
     for (int s = 0; s < 4; ++s) { tc::mbar_init(&y_full[s], 1); tc::mbar_init(&y_empty[s], FT_EPI); }
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc<128>(tmem_slot);
+  if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // PROD: 512 threads start with 128 registers each; the epilogue needs ~170, so the single-lane warps
+  // (warpgroup 0) and the drain warps (warpgroup 3) hand theirs over.  Each role branch re-budgets on entry
+  // so that ptxas allocates per branch.   4 x 128 x (56 + 176 + 176 + 104) = 65536
+#define FT_REGS_PRODUCER() do { if (PROD) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n"); } while (0)
+#define FT_REGS_EPILOGUE() do { if (PROD) asm volatile("setmaxnreg.inc.sync.aligned.u32 176;\n"); } while (0)
+#define FT_REGS_DRAIN() do { if (PROD) asm volatile("setmaxnreg.dec.sync.aligned.u32 104;\n"); } while (0)
 
   // unit -> (cell tile, first gene tile, gene tile count)
   auto unit_info = [&](int unit, int& ct, int& gt0, int& ngt) {
@@ -156,6 +183,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
   };
 
   if (warp == 0) {
+    FT_REGS_PRODUCER();
     if (lane == 0) {
       // ===== TMA producer of the factor operands (L2-resident) =====
       uint32_t bs = 0, bph = 0, aph = 0;
@@ -176,7 +204,8 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
         }
       }
     }
-  } else if (warp == 11) {
+  } else if (warp == FT_W_Y) {
+    FT_REGS_PRODUCER();
     if (lane == 0) {
       // ===== TMA producer of the count tiles (HBM): runs y_stages tiles ahead of the epilogue,
       // independent of the MMA pipeline (ncu: the epilogue spent 10 % of its samples waiting for Y
@@ -197,6 +226,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
       }
     }
   } else if (warp == 1) {
+    FT_REGS_PRODUCER();
     if (lane == 0) {
       // ===== MMA issuer =====
       constexpr uint32_t idesc = tc::instr_desc(0, 0, 0, 0, FT_CELLS, FT_GENES);
@@ -226,16 +256,30 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == FT_W_RETIRE) {
+    FT_REGS_PRODUCER();
     if (lane == 0) {
-      // ===== TMA store warp: ships each finished residual tile; no CTA-wide barrier on this path =====
+      // ===== retire warp: ships each finished residual tile (TMA store; no CTA-wide barrier on this path)
+      // and, PROD, feeds the same shared-memory tile to the product UMMAs =====
+      constexpr uint32_t idesc_hi = tc::instr_desc(0, 0, 0, 0, FT_CELLS, 64);   // R_hi x [Q0_hi | Q0_lo]
+      constexpr uint32_t idesc_lo = tc::instr_desc(0, 0, 0, 0, FT_CELLS, 32);   // R_lo x Q0_hi
       uint32_t rb = 0, ntile = 0;
       uint32_t fph[2] = {0, 0};
+      uint32_t pb = 0;
+      uint32_t peph[2] = {0, 0};
       for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
         int ct, gt0, ngt;
         unit_info(unit, ct, gt0, ngt);
+        auto load_op = [&](uint32_t n, int gtile) {   // operand tile of global tile count n -> stage n & 1
+          const uint32_t st = n & 1u;
+          tc::mbar_wait_relaxed(&op_empty[st], ((n >> 1) & 1u) ^ 1u);
+          tc::mbar_arrive_expect_tx(&op_full[st], FT_OP_BYTES);
+          tc::tma_load_2d(&map_op, &op_full[st], op_buf + st * FT_OP_BYTES, gtile * FT_GENES, 0);
+        };
+        if (PROD) load_op(ntile, gt0);
         for (int g = 0; g < ngt; ++g, ++ntile) {
           const int gene0 = (gt0 + g) * FT_GENES;
+          if (PROD && g + 1 < ngt) load_op(ntile + 1, gt0 + g + 1);   // one tile ahead: its stage was released a tile ago
           tc::mbar_wait_relaxed(&r_full[rb], fph[rb]);     // all 8 epilogue warps wrote (and proxy-fenced) their part
           fph[rb] ^= 1;
           uint8_t* rt = r_buf + rb * FT_R_BYTES;
@@ -244,18 +288,81 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
           tc::tma_store_commit();
           tc::tma_store_wait_read<1>();                    // the previous tile's store has drained the other buffer
           if (ntile >= 1) tc::mbar_arrive(&r_free[rb ^ 1]);
+          if (PROD) {
+            const uint32_t st = ntile & 1u;
+            if ((g & 1) == 0) { tc::mbar_wait(&p_empty[pb], peph[pb] ^ 1); peph[pb] ^= 1; }
+            tc::mbar_wait(&op_full[st], (ntile >> 1) & 1u);
+            tc::fence_after_sync();
+            const uint32_t a_hi = tc::smem_u32(rt), a_lo = a_hi + FT_CELLS * 128, bt = tc::smem_u32(op_buf + st * FT_OP_BYTES);
+            const uint32_t d = tmem_base + 128 + pb * 64;
+#pragma unroll
+            for (int ks = 0; ks < FT_GENES / 16; ++ks) {
+              const uint64_t da_hi = tc::smem_desc_sw128(a_hi + ks * 32, 16, 1024);
+              const uint64_t da_lo = tc::smem_desc_sw128(a_lo + ks * 32, 16, 1024);
+              const uint64_t dbd = tc::smem_desc_sw128(bt + ks * 32, 16, 1024);
+              tc::mma_f16(d, da_hi, dbd, idesc_hi, ((g & 1) || ks > 0) ? 1u : 0u);
+              tc::mma_f16(d, da_lo, dbd, idesc_lo, 1u);
+            }
+            tc::mma_commit(&op_empty[st]);
+            tc::mma_commit(&r_free[rb]);
+            if ((g & 1) || g == ngt - 1) { tc::mma_commit(&p_full[pb]); pb ^= 1; }
+          }
           rb ^= 1;
         }
       }
       tc::tma_store_wait<0>();
     }
+  } else if (PROD && warp >= FT_W_DRAIN0) {
+    // ===== PROD drain warps: thread = one cell; every pair of gene tiles the fp32 TMEM accumulator
+    // ([R_hi Q_hi + R_lo Q_hi | R_hi Q_lo], 2 x 32 columns) is folded into 32 fp64 registers =====
+    FT_REGS_DRAIN();
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    double acc[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+    uint32_t pbuf = 0;
+    uint32_t pfph[2] = {0, 0};
+    const double sc = (double)__ldg(p.op_inv) / (double)p.rscale;
+    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+      int ct, gt0, ngt;
+      unit_info(unit, ct, gt0, ngt);
+      const int npair = (ngt + 1) >> 1;
+      for (int pr = 0; pr < npair; ++pr) {
+        tc::mbar_wait_relaxed(&p_full[pbuf], pfph[pbuf]);
+        pfph[pbuf] ^= 1;
+        tc::fence_after_sync();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 128 + pbuf * 64;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v0[16], v1[16];
+          tc::tmem_ld16(taddr + h * 16, v0);
+          tc::tmem_ld16(taddr + 32 + h * 16, v1);
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int k = 0; k < 16; ++k) acc[h * 16 + k] += (double)__uint_as_float(v0[k]) + (double)__uint_as_float(v1[k]);
+        }
+        tc::fence_before_sync();
+        tc::mbar_arrive(&p_empty[pbuf]);
+        pbuf ^= 1;
+      }
+      const int64_t cell = (int64_t)ct * FT_CELLS + row;
+      if (cell < p.J) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if (k < p.prod_b) p.prod_out[(int64_t)k * p.prod_ld + cell] = acc[k] * sc;
+      }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+    }
   } else {
     // ===== epilogue: one cell per thread, 2 chunks of 16 genes per tile =====
-    const int e = warp - 2;                 // 0..7
+    FT_REGS_EPILOGUE();
+    const int e = warp - FT_W_EPI0;         // 0..7
     const int q = warp & 3;                 // TMEM lane quarter of this warp
     const int ch = e >> 2;                  // column half: genes ch*32 .. ch*32+31 of the tile
     const int row = q * 32 + lane;          // tile-local cell
-    const int et = threadIdx.x - 64;        // 0..255
+    const int et = threadIdx.x - FT_W_EPI0 * 32;   // 0..255
     const float inv = __ldg(p.inv_a) * __ldg(p.inv_b);
     const float L2E = 1.4426950408889634f * inv;   // log2(e) / (sA sB): one rounding of the product, <= 2^-24 |t|
     const float clampv = 8.0f / inv;
@@ -415,7 +522,10 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) { tc::fence_after_sync(); tc::tmem_dealloc<128>(tmem_base); }
+  if (warp == 1) { tc::fence_after_sync(); tc::tmem_dealloc<TMEM_COLS>(tmem_base); }
+#undef FT_REGS_PRODUCER
+#undef FT_REGS_EPILOGUE
+#undef FT_REGS_DRAIN
 }
 
 // out[1] += sum_i alpha_i rs_i + sum_j beta_j cs_j   (single CTA, fp64, fixed order)
@@ -607,9 +717,22 @@ bool eta_tc_supported(const PassGeom& g, const XDesc& x, int y_storage) {
   return true;
 }
 
+// the fused first Krylov pass needs: the unclamped low-rank X, one unit per cell tile still filling the GPU,
+// and room for the operand ring beside at least two count stages
+bool fused_prod_supported(Ctx& ctx, const PassGeom& g, const XDesc& x) {
+  const char* knob = getenv("SCGBM_FUSED_PROD");   // "0": off; "force": also below the size threshold (tests)
+  if ((knob && knob[0] == '0') || x.clamp || !x.A16) return false;
+  const int64_t n_cell_tiles = ceil_div(g.J, FT_CELLS);
+  if (n_cell_tiles < (int64_t)ctx.num_sms * 4 && !(knob && knob[0] == 'f')) return false;
+  const int nslab = x.A16->Kp / 64;
+  const int fixed = nslab * FT_SLAB_A + FT_NB * nslab * FT_SLAB_B + 2 * FT_R_BYTES + 1024 + 576 + 4 * FT_GENES * 4 + 2 * FT_OP_BYTES;
+  return (232448 - fixed) / (FT_CELLS * FT_GENES * 2) >= 2;
+}
+
 void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const Counts& y, const float* f_row,
                    const float* g_col, const float* la_row, const float* lb_col, const double* alpha,
-                   const double* beta, const double* rowsum_local, float maxY, ResidBuf resid, double* out3) {
+                   const double* beta, const double* rowsum_local, float maxY, ResidBuf resid, double* out3,
+                   const FusedProd* prod) {
   const Factor16& fa = *x.A16;
   const Factor16& fb = *x.B16;
   FusedTcParams p;
@@ -634,13 +757,19 @@ void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const
     }
   }
   if (getenv("SCGBM_FUSED_CHUNKS")) chunks = std::max(1, atoi(getenv("SCGBM_FUSED_CHUNKS")));   // experiments
+  const bool do_prod = prod != nullptr;
+  if (do_prod) {
+    SCGBM_REQUIRE(fused_prod_supported(ctx, g, x) && prod->b >= 1 && prod->b <= 32, "fused_tc: product fusion not available for this shape");
+    chunks = 1;   // one unit owns a cell tile's whole product row: fixed summation order, no atomics
+  }
   p.gene_tiles_per_unit = (int)ceil_div(p.n_gene_tiles, chunks);
   chunks = (int)ceil_div(p.n_gene_tiles, p.gene_tiles_per_unit);
   p.n_units = p.n_cell_tiles * chunks;
   const int ybytes = y.elem_bytes();
   p.y_stage_bytes = FT_CELLS * FT_GENES * ybytes;
-  const int fixed = p.nslab * FT_SLAB_A + FT_NB * p.nslab * FT_SLAB_B + 2 * FT_R_BYTES + 1024 + 512 + 4 * FT_GENES * 4;   // 512: barriers + CTA reduction scratch
-  p.y_stages = std::min(4, (int)((225 * 1024 - fixed) / p.y_stage_bytes));
+  const int fixed = p.nslab * FT_SLAB_A + FT_NB * p.nslab * FT_SLAB_B + 2 * FT_R_BYTES + 1024 + 576 + 4 * FT_GENES * 4 +
+                    (do_prod ? 2 * FT_OP_BYTES : 0);   // 576: barriers + CTA reduction scratch
+  p.y_stages = std::min(4, (int)(((do_prod ? 232448 : 225 * 1024) - fixed) / p.y_stage_bytes));
   SCGBM_REQUIRE(p.y_stages >= 2, "fused_tc: not enough shared memory for this M");
   const int smem_bytes = fixed + p.y_stages * p.y_stage_bytes;
   p.f_row = f_row; p.g_col = g_col; p.la_row = la_row; p.lb_col = lb_col;
@@ -656,17 +785,23 @@ void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const
                                       ybytes == 2 ? 128 : 0);
   const CUtensorMap mh = make_tmap_2d(resid.hi, 2, false, (uint64_t)g.ldI, (uint64_t)g.J, (uint64_t)g.ldI * 2, FT_GENES, FT_CELLS, 128);
   const CUtensorMap ml = make_tmap_2d(resid.lo, 2, false, (uint64_t)g.ldI, (uint64_t)g.J, (uint64_t)g.ldI * 2, FT_GENES, FT_CELLS, 128);
+  CUtensorMap mo = ml;   // unused without PROD
+  if (do_prod) {
+    p.prod_b = prod->b; p.prod_out = prod->out; p.prod_ld = prod->ldo; p.op_inv = prod->op_inv;
+    mo = make_tmap_2d(prod->op16, 2, false, (uint64_t)prod->ldk, 64, (uint64_t)prod->ldk * 2, 64, 64, 128);
+  }
   {
     ProfScope ps(ctx.prof, SCGBM_K_FUSED, 1);
-#define LAUNCH_FUSED(YT, CL, MBF)                                                                                          \
-  do {                                                                                                                     \
-    SCGBM_CUDA(cudaFuncSetAttribute(fused_tc_kernel<YT, CL, MBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
-    fused_tc_kernel<YT, CL, MBF><<<grid, FT_NT, smem_bytes, ctx.stream>>>(mc, mg, my, mh, ml, p);                            \
+#define LAUNCH_FUSED(YT, CL, MBF, PR)                                                                                          \
+  do {                                                                                                                         \
+    SCGBM_CUDA(cudaFuncSetAttribute(fused_tc_kernel<YT, CL, MBF, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
+    fused_tc_kernel<YT, CL, MBF, PR><<<grid, PR ? FT_NT_PROD : FT_NT, smem_bytes, ctx.stream>>>(mc, mg, my, mh, ml, mo, p);                        \
   } while (0)
-#define LAUNCH_FUSED_Y(YT)                                                                     \
-  do {                                                                                         \
-    if (mb) { if (x.clamp) LAUNCH_FUSED(YT, true, true); else LAUNCH_FUSED(YT, false, true); } \
-    else { if (x.clamp) LAUNCH_FUSED(YT, true, false); else LAUNCH_FUSED(YT, false, false); }  \
+#define LAUNCH_FUSED_Y(YT)                                                                                   \
+  do {                                                                                                       \
+    if (do_prod) { if (mb) LAUNCH_FUSED(YT, false, true, true); else LAUNCH_FUSED(YT, false, false, true); } \
+    else if (mb) { if (x.clamp) LAUNCH_FUSED(YT, true, true, false); else LAUNCH_FUSED(YT, false, true, false); } \
+    else { if (x.clamp) LAUNCH_FUSED(YT, true, false, false); else LAUNCH_FUSED(YT, false, false, false); }  \
   } while (0)
     const bool mb = g.nbatch > 1;
     if (ybytes == 2) LAUNCH_FUSED_Y(uint16_t); else LAUNCH_FUSED_Y(uint8_t);

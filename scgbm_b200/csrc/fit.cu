@@ -209,6 +209,8 @@ struct FitState {
   Factor slot[3];
   EtaWs eta;
   TsvdWs svd;
+  ProdWs fuse_ws;           // fp16 planes of the SVD's start block for the fused pass's product rider
+  DevBuf<double> RtQ0;      // ldJ x b: R^T Q0 delivered by the fused pass
   double maxY = 0;
   PassGeom geom;
 
@@ -476,7 +478,25 @@ struct FitRun {
       const bool x0 = fc.kind == XK_X0 || (prev >= 0 && prev != cur && st.slot[prev].kind == XK_X0);
       st.rscale = resid_scale_for(st.maxY * (x0 ? 1.0 + 10.0 / std::min(lr, 1.0) : 1.0));
     }
-    if (tc_eta)
+    // When this iteration's SVD will start from the previous left Ritz block Q0, the fused pass also
+    // delivers R^T Q0 -- the SVD's first pass over the residual -- from the tiles it has in shared memory.
+    bool rider = false;
+    if (tc_eta && fc.kind == XK_LOWRANK && !(prev >= 0 && prev != cur && st.slot[prev].kind == XK_X0)) {
+      int b = 0;
+      const double* Q0 = tsvd_left_start(st.svd, I, st.J_total, st.opts(), &b);
+      if (Q0 && b <= 32 && prod_uses_tc(b) && st.opts().variant == PROD_AUTO && fused_prod_supported(ctx, st.geom, xc)) {
+        split_operand(ctx, st.fuse_ws, ldI, b, 32, ldI, Q0, ldI);
+        if (st.RtQ0.n < ldJ * b) { st.RtQ0.alloc(ldJ * b); st.RtQ0.zero(ctx.stream); }
+        FusedProd fp;
+        fp.op16 = st.fuse_ws.op16.get(); fp.ldk = ldI; fp.op_inv = st.fuse_ws.opmeta.get() + 1; fp.b = b;
+        fp.out = st.RtQ0.get(); fp.ldo = ldJ;
+        pass_fused_tc(ctx, st.eta, st.geom, xc, st.Y, st.f_row.get(), st.g_col.get(), st.la_row.get(), st.lb_col.get(),
+                      st.alpha.get(), st.beta.get(), st.rs_local.get(), (float)st.maxY, st.resid(), st.scal.get(), &fp);
+        rider = true;
+      }
+    }
+    if (rider) {
+    } else if (tc_eta)
       pass_fused_tc(ctx, st.eta, st.geom, xc, st.Y, st.f_row.get(), st.g_col.get(), st.la_row.get(), st.lb_col.get(),
                     st.alpha.get(), st.beta.get(), st.rs_local.get(), (float)st.maxY, st.resid(), st.scal.get());
     else
@@ -534,6 +554,7 @@ struct FitRun {
     GOperator op;
     op.I = I; op.ldI = ldI; op.J = J; op.ldJ = ldJ; op.J_total = st.J_total;
     op.R = st.resid(); op.c = c; op.nterms = 0;
+    op.RtQ0 = rider ? st.RtQ0.get() : nullptr;
     auto add_term = [&](int s, double coef) {
       if (s < 0 || coef == 0.0) return;
       Factor& f = st.slot[s];

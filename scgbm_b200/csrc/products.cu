@@ -133,6 +133,8 @@ static bool use_tc(int variant, int b) {
   return !force_ffma && prod_tc_supported(b);
 }
 
+bool prod_uses_tc(int b) { return use_tc(PROD_AUTO, b); }
+
 void prod_n(Ctx& ctx, ProdWs& ws, ResidBuf R, int64_t I, int64_t ldI, int64_t J, const double* P,
             int64_t ldP, int b, double c, double* out, int64_t ldo, int variant, bool use_lo) {
   (void)I;

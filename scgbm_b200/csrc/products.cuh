@@ -45,6 +45,11 @@ struct ProdWs {
   DevBuf<double> part;      // prod_n split-K partials  [nchunk][bp][ldI]
 };
 
+// tcgen05 path: ws.op16 <- the two scaled fp16 planes [2*bp][ldk] of the fp64 operand src (rows x b, ld),
+// ws.opmeta[1] <- 1 / scale  (device side; no host round trip)
+void split_operand(Ctx& ctx, ProdWs& ws, int64_t rows, int b, int bp, int64_t ldk, const double* src, int64_t ld);
+bool prod_uses_tc(int b);     // the dispatch prod_t / prod_n take for PROD_AUTO
+
 enum { PROD_AUTO = 0, PROD_FFMA = 1, PROD_TCGEN05 = 2 };
 
 // use_lo = false: the tcgen05 kernel reads only the hi plane (11-bit residual, half the bytes) --

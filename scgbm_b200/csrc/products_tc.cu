@@ -336,7 +336,7 @@ static void launch_tc(Ctx& ctx, const CUtensorMap& mh, const CUtensorMap& ml, co
   SCGBM_LAUNCH_CHECK();
 }
 
-static void split_operand(Ctx& ctx, ProdWs& ws, int64_t rows, int b, int bp, int64_t ldk, const double* src, int64_t ld) {
+void split_operand(Ctx& ctx, ProdWs& ws, int64_t rows, int b, int bp, int64_t ldk, const double* src, int64_t ld) {
   if (ws.op16.n < 2 * (int64_t)bp * ldk) ws.op16.alloc(2 * (int64_t)bp * ldk);
   if (ws.opmeta.n < 2) ws.opmeta.alloc(2);
   int* absmax = reinterpret_cast<int*>(ws.opmeta.get());

@@ -125,8 +125,39 @@ static void op_mul(Ctx& ctx, TsvdWs& ws, const GOperator& op, const double* P, i
   ctx.allreduce_sum(out, op.ldI * b);
 }
 
+__global__ void axpy_kernel(int64_t n, double c, const double* __restrict__ x, double* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += c * x[i];
+}
+
+__global__ void maxdiff_kernel(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+  double d = 0.0, m = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    d = fmax(d, fabs(a[i] - b[i]));
+    m = fmax(m, fabs(b[i]));
+  }
+  d = warp_max(d); m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) {   // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(d));
+    atomicMax(reinterpret_cast<unsigned long long*>(out + 1), (unsigned long long)__double_as_longlong(m));
+  }
+}
+
+static bool ustart_enabled() {
+  static const bool on = getenv("SCGBM_USTART") ? atoi(getenv("SCGBM_USTART")) != 0 : true;
+  return on;
+}
+
+const double* tsvd_left_start(const TsvdWs& ws, int64_t I, int64_t J_total, const TsvdOpts& o, int* b_out) {
+  const int64_t minIJ = std::min(I, J_total);
+  const int b = (int)std::min<int64_t>(o.M + std::max(o.extra, 0), minIJ);
+  if (b_out) *b_out = b;
+  if (!(ustart_enabled() && ws.warm && ws.b == b && ws.warm_calls >= 1)) return nullptr;
+  return ws.Ub.get();
+}
+
 static void op_tmul(Ctx& ctx, TsvdWs& ws, const GOperator& op, const double* Q, int64_t ldQ, int b, double* out,
-                    int variant) {
+                    int variant, const double* RtQ = nullptr) {
   // out (ldJ x b) = G^T Q  (local cells)
   SCGBM_CUDA(cudaMemsetAsync(out, 0, (size_t)op.ldJ * b * sizeof(double), ctx.stream));
   for (int t = 0; t < op.nterms; ++t) {
@@ -140,6 +171,23 @@ static void op_tmul(Ctx& ctx, TsvdWs& ws, const GOperator& op, const double* Q, 
       SCGBM_LAUNCH_CHECK();
     }
     ts_mul(ctx, op.J, lt.M, b, lt.B, lt.ldb, C, lt.M, out, op.ldJ, 1.0, 1.0);
+  }
+  if (RtQ && op.R.hi && op.c != 0.0) {
+    static const bool check = getenv("SCGBM_CHECK_FUSED") != nullptr;
+    if (check) {   // debugging aid: the rider of the fused pass against a plain pass over the planes
+      ws.Vb.zero(ctx.stream);
+      ws.est.zero(ctx.stream);
+      prod_t(ctx, ws.prod, op.R, op.I, op.ldI, op.J, Q, ldQ, b, 1.0, ws.Vb.get(), op.ldJ, variant, true);
+      maxdiff_kernel<<<256, 256, 0, ctx.stream>>>(op.ldJ * b, RtQ, ws.Vb.get(), ws.est.get());
+      double h[2];
+      SCGBM_CUDA(cudaMemcpyAsync(h, ws.est.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
+      ctx.sync();
+      fprintf(stderr, "[scgbm-check] fused R^T Q0: max |diff| %.3e, max |ref| %.3e\n", h[0], h[1]);
+    }
+    ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
+    axpy_kernel<<<(unsigned)ceil_div(op.ldJ * b, 256), 256, 0, ctx.stream>>>(op.ldJ * b, op.c, RtQ, out);
+    SCGBM_LAUNCH_CHECK();
+    return;
   }
   if (op.R.hi && op.c != 0.0) prod_t(ctx, ws.prod, op.R, op.I, op.ldI, op.J, Q, ldQ, b, op.c, out, op.ldJ, variant, !ws.lowprec);
 }
@@ -227,8 +275,7 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
     // parity-neutral (objective, alpha, angles unchanged to the digits printed), unlike hi-only Q1.
     static const bool env_start_full = getenv("SCGBM_START_FULL") != nullptr;
     ws.start_hi = was_warm && !env_start_full;
-    static const bool env_ustart = getenv("SCGBM_USTART") ? atoi(getenv("SCGBM_USTART")) != 0 : true;
-    const bool ustart = env_ustart && was_warm && ws.warm_calls >= 1;
+    const bool ustart = ustart_enabled() && was_warm && ws.warm_calls >= 1;
     for (int cycle = 0; !restart; ++cycle) {
       ws.T.zero(ctx.stream);
       if (ustart && cycle == 0) {
@@ -244,8 +291,10 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
       for (int t = 0;; ++t) {
         p = b * (t + 1);
         double* Zt = ws.Zb.get() + (int64_t)t * b * ldJ;
-        op_tmul(ctx, ws, op, ws.Qb.get() + (int64_t)t * b * ldI, ldI, b, Zt, o.variant);
-        ++passes;
+        // the first block of a call started from the previous left Ritz block may have been multiplied already
+        const bool have = ustart && cycle == 0 && t == 0 && op.RtQ0 != nullptr;
+        op_tmul(ctx, ws, op, ws.Qb.get() + (int64_t)t * b * ldI, ldI, b, Zt, o.variant, have ? op.RtQ0 : nullptr);
+        if (!have) ++passes;
         // Gram block column  Zb[:, :p]^T Z_t  (p x b), all ranks
         ts_gram(ctx, ws.small, op.J, p, b, ws.Zb.get(), ldJ, Zt, ldJ, ws.C.get(), p, 1.0, 0.0);
         ctx.allreduce_sum(ws.C.get(), (int64_t)p * b);

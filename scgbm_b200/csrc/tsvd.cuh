@@ -25,6 +25,9 @@ struct GOperator {
   double c = 0.0;
   int nterms = 0;
   LowRankTerm t[2];
+  // R^T Q0 (ldJ x b) for Q0 = the start block tsvd_left_start() announced, computed by the fused
+  // likelihood pass that produced R (eta_pass.cuh: FusedProd); nullptr: tsvd reads the planes itself
+  const double* RtQ0 = nullptr;
 };
 
 struct TsvdOpts {
@@ -60,6 +63,10 @@ struct TsvdWs {
 // outU: ldI x M, outD: M, outV: ldJ x M (device, column-major)
 // upload a J x b start block (host, column-major) as the warm start of the next call
 void tsvd_set_warm_start(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, const double* V0_host);
+
+// The next warm call starts its Krylov space from a left block that is already known (the previous
+// call's left Ritz block): returns it (ldI x *b) or nullptr when the next call starts differently.
+const double* tsvd_left_start(const TsvdWs& ws, int64_t I, int64_t J_total, const TsvdOpts& o, int* b);
 
 void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* outU, double* outD,
           double* outV, int* passes_out, double* est_out);

@@ -12,9 +12,17 @@ from . import _lib as L
 
 
 def gbm_proj_parallel(Y, M, subsample=2000, min_counts=5, ncores=1, tol=1e-4, max_iter=100, *,
-                      device=-1, rng=None, profile=False, svd_tol=0.0, seed=0, glm_tol=1e-8, glm_maxit=100):
+                      device=-1, rng=None, profile=False, svd_tol=0.0, seed=0, glm_tol=1e-8, glm_maxit=100,
+                      comm=None, subsample_Y=None):
+    """Cells sharded over ranks (BASELINE configs[3]): pass `comm` and the
+    subsample's count matrix `subsample_Y` (I x s, the same on every rank -- the host
+    harness gathers those columns).  Y then holds this rank's cells only; every rank
+    runs the identical subsample fit (bit-reproducible), projects its own cells, and the
+    only exchanges are the gene row sums and the scalar sum(exp(beta)) of R/fit.R:274."""
     from .api import gbm_sc, _as_counts, _is_sparse, _NP2DT
     lib = L.load()
+    if (comm is None) != (subsample_Y is None):
+        raise ValueError("comm and subsample_Y go together")
     sparse = _is_sparse(Y)
     if sparse:                       # dgCMatrix-style input stays sparse on the host (R/fit.R:224 densifies only Y.sub)
         Ys = Y.tocsc()
@@ -24,14 +32,23 @@ def gbm_proj_parallel(Y, M, subsample=2000, min_counts=5, ncores=1, tol=1e-4, ma
         Yh, y_dt = _as_counts(Y)
         I, J = Yh.shape
         rs = Yh.sum(axis=1, dtype=np.float64)
+    if comm is not None:
+        rs = comm.allreduce(rs)
     with np.errstate(divide="ignore"):
         alphas_full = np.log(rs)                                           # R/fit.R:217
-    if np.ndim(subsample) == 0:                                            # R/fit.R:218-220
+    if subsample_Y is not None:
+        jxs = None
+    elif np.ndim(subsample) == 0:                                            # R/fit.R:218-220
         rng = rng or np.random.default_rng()
         jxs = rng.choice(J, size=int(subsample), replace=False)            # sample(1:J, size)
     else:
         jxs = np.asarray(subsample, dtype=np.int64) - 1                    # 1-based like R (:221-223)
-    Y_sub = np.asfortranarray(Ys[:, jxs].toarray() if sparse else Yh[:, jxs])   # as.matrix(Y.sub)  :224
+    if subsample_Y is not None:
+        Y_sub = subsample_Y.toarray() if _is_sparse(subsample_Y) else np.asarray(subsample_Y)
+        if Y_sub.shape[0] != I:
+            raise ValueError("subsample_Y must have the same genes as Y")
+    else:
+        Y_sub = np.asfortranarray(Ys[:, jxs].toarray() if sparse else Yh[:, jxs])   # as.matrix(Y.sub)  :224
     ixs = np.nonzero(Y_sub.sum(axis=1, dtype=np.float64) > 5)[0]           # hard-coded 5  :225
     Y_sub = np.asfortranarray(Y_sub[ixs, :])
     out = gbm_sc(Y_sub, M, tol=tol, max_iter=max_iter, device=device, profile=profile,
@@ -63,7 +80,10 @@ def gbm_proj_parallel(Y, M, subsample=2000, min_counts=5, ncores=1, tol=1e-4, ma
     alpha[ixs] = out["alpha"][:, 0]                                        # :273
     mask = np.ones(I, dtype=bool); mask[ixs] = False
     with np.errstate(over="ignore"):
-        alpha[mask] = alphas_full[mask] - np.log(np.exp(beta).sum())       # :274
+        sum_eb = np.exp(beta).sum()
+        if comm is not None:
+            sum_eb = float(comm.allreduce(np.array([sum_eb]))[0])
+        alpha[mask] = alphas_full[mask] - np.log(sum_eb)                   # :274
     am = alpha.mean()
     out["beta"] = beta + am                                                # :275
     out["alpha"] = alpha - am                                              # :276-277

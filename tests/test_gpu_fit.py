@@ -311,3 +311,24 @@ def test_stepwise_handle_equals_one_shot():
     assert o.n_iter == ref["_n_iter"] == trips
     np.testing.assert_array_equal(obj[: o.n_obj], ref["obj"])
     np.testing.assert_array_equal(U, ref["U"])
+
+
+@pytest.mark.parametrize("I,J,d,M,kw,gen", [CASES[2], CASES[6], (257, 1031, 8, 8, dict(infer_beta=True), dict(nb=1.0))])
+def test_fused_product_rider_matches_plain_pass(I, J, d, M, kw, gen, monkeypatch):
+    """The fused pass's rider (R^T Q0 from the residual tiles in shared memory; eta_tc.cu PROD) replaces the
+    warm SVD's first pass over the planes: same tiles, same operand planes, same drain cadence as prod_t."""
+    from scgbm_b200 import gbm_sc
+    from oracle.scgbm_oracle import gbm_sc as o_gbm_sc
+    from tests.util import principal_angle
+    Y = _sim(I, J, d, seed=I + J, **gen)
+    monkeypatch.setenv("SCGBM_FUSED_PROD", "0")
+    plain = gbm_sc(Y, M, diagnostics=True, **kw)
+    monkeypatch.setenv("SCGBM_FUSED_PROD", "force")
+    rider = gbm_sc(Y, M, diagnostics=True, **kw)
+    assert rider["_prof"]["svd_passes"] < plain["_prof"]["svd_passes"]          # the rider really ran
+    n = min(len(plain["_LL"]), len(rider["_LL"]))
+    np.testing.assert_array_equal(plain["_accepted"][:n], rider["_accepted"][:n])
+    np.testing.assert_allclose(rider["_LL"][:n], plain["_LL"][:n], rtol=1e-9)
+    np.testing.assert_allclose(rider["alpha"], plain["alpha"], atol=1e-7)
+    assert principal_angle(rider["U"], plain["U"]) < 1e-5
+    assert assert_fit_parity(o_gbm_sc(Y, M, **kw), rider) in ("full", "knife-edge")

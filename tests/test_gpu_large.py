@@ -33,3 +33,22 @@ def test_large_fit_invariants_and_reproducibility():
     assert np.abs(a["V"].T @ a["V"] - np.eye(M)).max() < 1e-10
     assert np.all(np.diff(a["D"]) <= 0) and np.all(a["U"][0] >= 0)
     np.testing.assert_allclose(a["scores"], a["V"] * a["D"][None, :], rtol=0, atol=0)
+
+
+def test_large_fit_with_product_rider(monkeypatch):
+    """Full-height genes (313 gene tiles per unit, 157 accumulator drains) through the fused pass's product
+    rider against the plain first pass; the rider is also bit-reproducible (one unit per cell tile)."""
+    from scgbm_b200 import gbm_sc
+    I, J, M = 20000, 40000, 20
+    Y = _device_counts(I, J, M)
+    monkeypatch.setenv("SCGBM_FUSED_PROD", "0")
+    plain = gbm_sc(Y, M, max_iter=10, return_W=False, diagnostics=True)
+    monkeypatch.setenv("SCGBM_FUSED_PROD", "force")
+    a = gbm_sc(Y, M, max_iter=10, return_W=False, diagnostics=True)
+    b = gbm_sc(Y, M, max_iter=10, return_W=False, diagnostics=True)
+    assert a["_prof"]["svd_passes"] < plain["_prof"]["svd_passes"]
+    np.testing.assert_array_equal(a["_LL"], b["_LL"])
+    np.testing.assert_array_equal(a["U"], b["U"])
+    np.testing.assert_array_equal(a["_accepted"], plain["_accepted"])
+    np.testing.assert_allclose(a["_LL"], plain["_LL"], rtol=1e-9)
+    np.testing.assert_allclose(a["alpha"], plain["alpha"], atol=1e-7)
