@@ -89,6 +89,8 @@ constexpr int FT_NT_PROD = 512;       // + warps 12-15: fp64 drain of the produc
 constexpr int FT_W_RETIRE = 2, FT_W_Y = 3, FT_W_EPI0 = 4, FT_W_DRAIN0 = 12;
 constexpr int FT_OP_BYTES = 64 * 128; // fused product: one operand tile, [hi 32 | lo 32 block columns][64 genes] fp16
 constexpr int FT_NB = 3;              // gene-operand ring depth
+constexpr int FT_NB_PROD = 2;         // ... with the product rider: one stage goes to the operand ring
+constexpr int FT_NOP = 4;             // product operand ring depth (tiles are requested 3 ahead)
 constexpr int FT_EPI = 256;
 constexpr int FT_CELLS = 128;         // MMA M  (TMEM lanes = cells)
 constexpr int FT_GENES = 64;          // MMA N  (TMEM columns = genes)
@@ -112,6 +114,7 @@ struct FusedTcParams {
   int prod_b;                         // block columns (<= 32)
   double* prod_out; int64_t prod_ld;  // J x prod_b, column-major
   const float* op_inv;                // device: 1 / operand scale
+  uint32_t ns_prod, ns_mma, ns_drain; // back-off of the polling single-lane warps / UMMA issuer (0: spin) / drain warps
 };
 
 // PROD: the tile that the epilogue just wrote to shared memory for the TMA store is, as it lies there
@@ -130,20 +133,21 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_buf = smem;                                          // nslab * 16 KB (cells)
   uint8_t* b_buf = a_buf + p.nslab * FT_SLAB_A;                   // FT_NB * nslab * 8 KB (genes)
-  uint8_t* y_buf = b_buf + FT_NB * p.nslab * FT_SLAB_B;           // y_stages * y_stage_bytes
+  constexpr int NB = PROD ? FT_NB_PROD : FT_NB;
+  uint8_t* y_buf = b_buf + NB * p.nslab * FT_SLAB_B;              // y_stages * y_stage_bytes
   uint8_t* r_buf = y_buf + p.y_stages * p.y_stage_bytes;          // 2 * 32 KB
-  uint8_t* op_buf = r_buf + 2 * FT_R_BYTES;                       // PROD: 2 * 8 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(op_buf + (PROD ? 2 * FT_OP_BYTES : 0));
+  uint8_t* op_buf = r_buf + 2 * FT_R_BYTES;                       // PROD: FT_NOP * 8 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(op_buf + (PROD ? FT_NOP * FT_OP_BYTES : 0));
   uint64_t* a_full = bars;        uint64_t* a_empty = bars + 1;
   uint64_t* b_full = bars + 2;    uint64_t* b_empty = bars + 5;   // [FT_NB]
   uint64_t* d_full = bars + 8;    uint64_t* d_empty = bars + 10;  // [2]
   uint64_t* y_full = bars + 12;   uint64_t* y_empty = bars + 16;  // [<=4]
   uint64_t* r_full = bars + 20;   uint64_t* r_free = bars + 22;   // [2] residual tile buffers: epilogue <-> store warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
-  uint64_t* op_full = bars + 26;  uint64_t* op_empty = bars + 28; // [2] PROD: operand tiles, retire warp <-> tensor core
-  uint64_t* p_full = bars + 30;   uint64_t* p_empty = bars + 32;  // [2] PROD: product accumulators, tensor core <-> epilogue
-  double* red = reinterpret_cast<double*>(bars + 34);             // [8][4]
-  float* f_ring = reinterpret_cast<float*>(bars + 66);            // [<=4][64] exp(alpha_i) of the gene tile, with each Y stage
+  uint64_t* op_full = bars + 26;  uint64_t* op_empty = bars + 30; // [FT_NOP] PROD: operand tiles, retire warp <-> tensor core
+  uint64_t* p_full = bars + 34;   uint64_t* p_empty = bars + 36;  // [2] PROD: product accumulators, tensor core <-> drain warps
+  double* red = reinterpret_cast<double*>(bars + 38);             // [8][4]
+  float* f_ring = reinterpret_cast<float*>(bars + 70);            // [<=4][64] exp(alpha_i) of the gene tile, with each Y stage
   constexpr int TMEM_COLS = PROD ? 256 : 128;                     // eta x2 at 0/64; PROD: products x2 at 128/192
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -152,13 +156,13 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
     tc::tma_prefetch_desc(&map_hi); tc::tma_prefetch_desc(&map_lo);
     if (PROD) tc::tma_prefetch_desc(&map_op);
     tc::mbar_init(a_full, 1); tc::mbar_init(a_empty, 1);
-    for (int s = 0; s < FT_NB; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < NB; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&d_full[s], 1); tc::mbar_init(&d_empty[s], FT_EPI);
       tc::mbar_init(&r_full[s], 8); tc::mbar_init(&r_free[s], PROD ? 2 : 1);   // PROD: store drained + product UMMAs done
-      tc::mbar_init(&op_full[s], 1); tc::mbar_init(&op_empty[s], 1);
       tc::mbar_init(&p_full[s], 1); tc::mbar_init(&p_empty[s], 128);
     }
+    for (int s = 0; s < FT_NOP; ++s) { tc::mbar_init(&op_full[s], 1); tc::mbar_init(&op_empty[s], 1); }
     for (int s = 0; s < 4; ++s) { tc::mbar_init(&y_full[s], 1); tc::mbar_init(&y_empty[s], FT_EPI); }
     tc::fence_barrier_init();
   }
@@ -190,17 +194,17 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
       for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
         int ct, gt0, ngt;
         unit_info(unit, ct, gt0, ngt);
-        tc::mbar_wait_relaxed(a_empty, aph ^ 1);
+        tc::mbar_wait_relaxed(a_empty, aph ^ 1, p.ns_prod);
         tc::mbar_arrive_expect_tx(a_full, p.nslab * FT_SLAB_A);
         for (int s = 0; s < p.nslab; ++s) tc::tma_load_2d(&map_cells, a_full, a_buf + s * FT_SLAB_A, s * 64, ct * FT_CELLS);
         aph ^= 1;
         for (int g = 0; g < ngt; ++g) {
           const int gene0 = (gt0 + g) * FT_GENES;
-          tc::mbar_wait_relaxed(&b_empty[bs], bph ^ 1);
+          tc::mbar_wait_relaxed(&b_empty[bs], bph ^ 1, p.ns_prod);
           tc::mbar_arrive_expect_tx(&b_full[bs], p.nslab * FT_SLAB_B);
           for (int s = 0; s < p.nslab; ++s)
             tc::tma_load_2d(&map_genes, &b_full[bs], b_buf + (bs * p.nslab + s) * FT_SLAB_B, s * 64, gene0);
-          if (++bs == FT_NB) { bs = 0; bph ^= 1; }
+          if (++bs == NB) { bs = 0; bph ^= 1; }
         }
       }
     }
@@ -215,7 +219,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
         int ct, gt0, ngt;
         unit_info(unit, ct, gt0, ngt);
         for (int g = 0; g < ngt; ++g) {
-          tc::mbar_wait_relaxed(&y_empty[ys], yph ^ 1);
+          tc::mbar_wait_relaxed(&y_empty[ys], yph ^ 1, p.ns_prod);
           // f_i rides along with the count tile (single batch): the 80 KB vector does not survive in the
           // ~14 KB of L1 left beside 214 KB of shared memory, and an L2 round trip per chunk stalls the epilogue
           tc::mbar_arrive_expect_tx(&y_full[ys], p.y_stage_bytes + (MB ? 0 : FT_GENES * 4));
@@ -238,8 +242,13 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
         tc::mbar_wait(a_full, aph);
         aph ^= 1;
         for (int g = 0; g < ngt; ++g) {
-          tc::mbar_wait(&d_empty[db], dph[db] ^ 1);
-          tc::mbar_wait(&b_full[bs], bph);
+          if (p.ns_mma) {
+            tc::mbar_wait_relaxed(&d_empty[db], dph[db] ^ 1, p.ns_mma);
+            tc::mbar_wait_relaxed(&b_full[bs], bph, p.ns_mma);
+          } else {
+            tc::mbar_wait(&d_empty[db], dph[db] ^ 1);
+            tc::mbar_wait(&b_full[bs], bph);
+          }
           tc::fence_after_sync();
           const uint32_t a0 = tc::smem_u32(a_buf), b0 = tc::smem_u32(b_buf + bs * p.nslab * FT_SLAB_B);
           const uint32_t d = tmem_base + db * FT_GENES;
@@ -252,7 +261,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
           tc::mma_commit(&d_full[db]);
           if (g == ngt - 1) tc::mma_commit(a_empty);
           dph[db] ^= 1; db ^= 1;
-          if (++bs == FT_NB) { bs = 0; bph ^= 1; }
+          if (++bs == NB) { bs = 0; bph ^= 1; }
         }
       }
     }
@@ -270,17 +279,19 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
       for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
         int ct, gt0, ngt;
         unit_info(unit, ct, gt0, ngt);
-        auto load_op = [&](uint32_t n, int gtile) {   // operand tile of global tile count n -> stage n & 1
-          const uint32_t st = n & 1u;
-          tc::mbar_wait_relaxed(&op_empty[st], ((n >> 1) & 1u) ^ 1u);
+        auto load_op = [&](uint32_t n, int gtile) {   // operand tile of global tile count n -> stage n % FT_NOP
+          const uint32_t st = n % FT_NOP;
+          tc::mbar_wait_relaxed(&op_empty[st], ((n / FT_NOP) & 1u) ^ 1u, p.ns_prod);
           tc::mbar_arrive_expect_tx(&op_full[st], FT_OP_BYTES);
           tc::tma_load_2d(&map_op, &op_full[st], op_buf + st * FT_OP_BYTES, gtile * FT_GENES, 0);
         };
-        if (PROD) load_op(ntile, gt0);
+        if (PROD)
+          for (int a = 0; a < FT_NOP - 1 && a < ngt; ++a) load_op(ntile + a, gt0 + a);
         for (int g = 0; g < ngt; ++g, ++ntile) {
           const int gene0 = (gt0 + g) * FT_GENES;
-          if (PROD && g + 1 < ngt) load_op(ntile + 1, gt0 + g + 1);   // one tile ahead: its stage was released a tile ago
-          tc::mbar_wait_relaxed(&r_full[rb], fph[rb]);     // all 8 epilogue warps wrote (and proxy-fenced) their part
+          // FT_NOP - 1 tiles ahead: that stage's last reader was issued one tile ago
+          if (PROD && g + FT_NOP - 1 < ngt) load_op(ntile + FT_NOP - 1, gt0 + g + FT_NOP - 1);
+          tc::mbar_wait_relaxed(&r_full[rb], fph[rb], p.ns_prod);     // all 8 epilogue warps wrote (and proxy-fenced) their part
           fph[rb] ^= 1;
           uint8_t* rt = r_buf + rb * FT_R_BYTES;
           tc::tma_store_2d(&map_hi, rt, gene0, ct * FT_CELLS);
@@ -289,9 +300,9 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
           tc::tma_store_wait_read<1>();                    // the previous tile's store has drained the other buffer
           if (ntile >= 1) tc::mbar_arrive(&r_free[rb ^ 1]);
           if (PROD) {
-            const uint32_t st = ntile & 1u;
+            const uint32_t st = ntile % FT_NOP;
             if ((g & 1) == 0) { tc::mbar_wait(&p_empty[pb], peph[pb] ^ 1); peph[pb] ^= 1; }
-            tc::mbar_wait(&op_full[st], (ntile >> 1) & 1u);
+            tc::mbar_wait(&op_full[st], (ntile / FT_NOP) & 1u);
             tc::fence_after_sync();
             const uint32_t a_hi = tc::smem_u32(rt), a_lo = a_hi + FT_CELLS * 128, bt = tc::smem_u32(op_buf + st * FT_OP_BYTES);
             const uint32_t d = tmem_base + 128 + pb * 64;
@@ -329,7 +340,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
       unit_info(unit, ct, gt0, ngt);
       const int npair = (ngt + 1) >> 1;
       for (int pr = 0; pr < npair; ++pr) {
-        tc::mbar_wait_relaxed(&p_full[pbuf], pfph[pbuf]);
+        tc::mbar_wait_relaxed(&p_full[pbuf], pfph[pbuf], p.ns_drain);
         pfph[pbuf] ^= 1;
         tc::fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 128 + pbuf * 64;
@@ -348,9 +359,10 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
       }
       const int64_t cell = (int64_t)ct * FT_CELLS + row;
       if (cell < p.J) {
+        double* dst = p.prod_out + cell;
 #pragma unroll
         for (int k = 0; k < 32; ++k)
-          if (k < p.prod_b) p.prod_out[(int64_t)k * p.prod_ld + cell] = acc[k] * sc;
+          if (k < p.prod_b) dst[(int64_t)k * p.prod_ld] = acc[k] * sc;
       }
 #pragma unroll
       for (int k = 0; k < 32; ++k) acc[k] = 0.0;
@@ -717,15 +729,16 @@ bool eta_tc_supported(const PassGeom& g, const XDesc& x, int y_storage) {
   return true;
 }
 
-// the fused first Krylov pass needs: the unclamped low-rank X, one unit per cell tile still filling the GPU,
-// and room for the operand ring beside at least two count stages
+// the fused first Krylov pass needs: the unclamped low-rank X, enough cell tiles to be worth it, and room
+// for the operand ring beside at least two count stages
 bool fused_prod_supported(Ctx& ctx, const PassGeom& g, const XDesc& x) {
   const char* knob = getenv("SCGBM_FUSED_PROD");   // "0": off; "force": also below the size threshold (tests)
   if ((knob && knob[0] == '0') || x.clamp || !x.A16) return false;
+  // one unit per cell tile (see pass_fused_tc): below ~4 tiles per SM the unfilled last wave eats the gain
   const int64_t n_cell_tiles = ceil_div(g.J, FT_CELLS);
   if (n_cell_tiles < (int64_t)ctx.num_sms * 4 && !(knob && knob[0] == 'f')) return false;
   const int nslab = x.A16->Kp / 64;
-  const int fixed = nslab * FT_SLAB_A + FT_NB * nslab * FT_SLAB_B + 2 * FT_R_BYTES + 1024 + 576 + 4 * FT_GENES * 4 + 2 * FT_OP_BYTES;
+  const int fixed = nslab * FT_SLAB_A + FT_NB_PROD * nslab * FT_SLAB_B + 2 * FT_R_BYTES + 1024 + 640 + 4 * FT_GENES * 4 + FT_NOP * FT_OP_BYTES;
   return (232448 - fixed) / (FT_CELLS * FT_GENES * 2) >= 2;
 }
 
@@ -760,15 +773,19 @@ void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const
   const bool do_prod = prod != nullptr;
   if (do_prod) {
     SCGBM_REQUIRE(fused_prod_supported(ctx, g, x) && prod->b >= 1 && prod->b <= 32, "fused_tc: product fusion not available for this shape");
-    chunks = 1;   // one unit owns a cell tile's whole product row: fixed summation order, no atomics
+    // One unit owns a cell tile's whole product row: fixed summation order, the very drain cadence of prod_t
+    // (bit-identical results), no partial buffers.  Measured alternative -- gene chunks with per-chunk partials
+    // summed afterwards -- fills the last wave better but pays the operand/accumulator ramp per unit:
+    // 4.0 vs ~3.5 ms at 125k cells.
+    chunks = 1;
   }
   p.gene_tiles_per_unit = (int)ceil_div(p.n_gene_tiles, chunks);
   chunks = (int)ceil_div(p.n_gene_tiles, p.gene_tiles_per_unit);
   p.n_units = p.n_cell_tiles * chunks;
   const int ybytes = y.elem_bytes();
   p.y_stage_bytes = FT_CELLS * FT_GENES * ybytes;
-  const int fixed = p.nslab * FT_SLAB_A + FT_NB * p.nslab * FT_SLAB_B + 2 * FT_R_BYTES + 1024 + 576 + 4 * FT_GENES * 4 +
-                    (do_prod ? 2 * FT_OP_BYTES : 0);   // 576: barriers + CTA reduction scratch
+  const int fixed = p.nslab * FT_SLAB_A + (do_prod ? FT_NB_PROD : FT_NB) * p.nslab * FT_SLAB_B + 2 * FT_R_BYTES + 1024 + 640 +
+                    4 * FT_GENES * 4 + (do_prod ? FT_NOP * FT_OP_BYTES : 0);   // 640: barriers + CTA reduction scratch
   p.y_stages = std::min(4, (int)(((do_prod ? 232448 : 225 * 1024) - fixed) / p.y_stage_bytes));
   SCGBM_REQUIRE(p.y_stages >= 2, "fused_tc: not enough shared memory for this M");
   const int smem_bytes = fixed + p.y_stages * p.y_stage_bytes;
@@ -776,6 +793,9 @@ void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const
   p.inv_a = fa.meta.get() + 1; p.inv_b = fb.meta.get() + 1;
   p.maxY = maxY; p.log_maxY = logf(maxY); p.rscale = resid.scale;
   p.batch = g.batch; p.rowscale = x.rowscale;
+  // polling back-off (ns): measured flat between 64 and 400 for the single-lane warps, with or without a
+  // back-off in the UMMA issuer; the drain warps poll once per ~3 us pair of tiles
+  p.ns_prod = 64; p.ns_mma = 0; p.ns_drain = 400;
   const int grid = std::min(p.n_units, ctx.num_sms);
   if (ws.scal_part.n < (int64_t)grid * 4) ws.scal_part.alloc((int64_t)grid * 4);
   p.scal_part = ws.scal_part.get();
@@ -788,6 +808,7 @@ void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const
   CUtensorMap mo = ml;   // unused without PROD
   if (do_prod) {
     p.prod_b = prod->b; p.prod_out = prod->out; p.prod_ld = prod->ldo; p.op_inv = prod->op_inv;
+
     mo = make_tmap_2d(prod->op16, 2, false, (uint64_t)prod->ldk, 64, (uint64_t)prod->ldk * 2, 64, 64, 128);
   }
   {

@@ -58,10 +58,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // same, for single-thread producer roles that may wait long: back off so that the spin does
 // not eat issue slots of the epilogue warps sharing the scheduler (ncu: 7 % of all issues)
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns = 64) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(64);
+    __nanosleep(ns);
     if (++spins > (1u << 24)) { printf("scgbm: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
   }
 }
