@@ -171,9 +171,12 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  // PROD: 512 threads start with 128 registers each; the epilogue needs ~170, so the single-lane warps
+  // PROD: 512 threads start with 128 registers each; the epilogue needs ~165, so the single-lane warps
   // (warpgroup 0) and the drain warps (warpgroup 3) hand theirs over.  Each role branch re-budgets on entry
   // so that ptxas allocates per branch.   4 x 128 x (56 + 176 + 176 + 104) = 65536
+  // (ptxas still aims near the launch value and rematerialises in the epilogue, ~134 registers used.  The
+  // alternative that keeps 384 threads -- the four role warps folding the accumulator while their roles
+  // wait -- was measured slower: 4.3 vs 3.1 ms per pass at 100k cells, the drains delay the roles.)
 #define FT_REGS_PRODUCER() do { if (PROD) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n"); } while (0)
 #define FT_REGS_EPILOGUE() do { if (PROD) asm volatile("setmaxnreg.inc.sync.aligned.u32 176;\n"); } while (0)
 #define FT_REGS_DRAIN() do { if (PROD) asm volatile("setmaxnreg.dec.sync.aligned.u32 104;\n"); } while (0)
@@ -186,31 +189,41 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
     ngt = min(p.gene_tiles_per_unit, p.n_gene_tiles - gt0);
   };
 
-  if (warp == 0) {
+  if (warp < 4) {
+    // ===== warpgroup 0: four roles, one elected lane each =====
     FT_REGS_PRODUCER();
-    if (lane == 0) {
-      // ===== TMA producer of the factor operands (L2-resident) =====
+    const bool lead = lane == 0;
+    const bool act = lead;
+    // role waits: ns == 0 spins (UMMA issuer), otherwise backs off so that the poll does not eat issue slots
+    auto pwait = [&](uint64_t* bar, uint32_t parity, uint32_t ns, bool) {
+      if (ns) tc::mbar_wait_relaxed(bar, parity, ns); else tc::mbar_wait(bar, parity);
+    };
+
+    if (warp == 0 && act) {
+      // ===== TMA producer of the factor operands (L2-resident); g = -1 is the unit's cell operand =====
       uint32_t bs = 0, bph = 0, aph = 0;
       for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
         int ct, gt0, ngt;
         unit_info(unit, ct, gt0, ngt);
-        tc::mbar_wait_relaxed(a_empty, aph ^ 1, p.ns_prod);
-        tc::mbar_arrive_expect_tx(a_full, p.nslab * FT_SLAB_A);
-        for (int s = 0; s < p.nslab; ++s) tc::tma_load_2d(&map_cells, a_full, a_buf + s * FT_SLAB_A, s * 64, ct * FT_CELLS);
-        aph ^= 1;
-        for (int g = 0; g < ngt; ++g) {
-          const int gene0 = (gt0 + g) * FT_GENES;
-          tc::mbar_wait_relaxed(&b_empty[bs], bph ^ 1, p.ns_prod);
-          tc::mbar_arrive_expect_tx(&b_full[bs], p.nslab * FT_SLAB_B);
-          for (int s = 0; s < p.nslab; ++s)
-            tc::tma_load_2d(&map_genes, &b_full[bs], b_buf + (bs * p.nslab + s) * FT_SLAB_B, s * 64, gene0);
-          if (++bs == NB) { bs = 0; bph ^= 1; }
+        for (int g = -1; g < ngt; ++g) {
+          pwait(g < 0 ? a_empty : &b_empty[bs], (g < 0 ? aph : bph) ^ 1, p.ns_prod, true);
+          if (g < 0) {
+            if (lead) {
+              tc::mbar_arrive_expect_tx(a_full, p.nslab * FT_SLAB_A);
+              for (int s = 0; s < p.nslab; ++s) tc::tma_load_2d(&map_cells, a_full, a_buf + s * FT_SLAB_A, s * 64, ct * FT_CELLS);
+            }
+            aph ^= 1;
+          } else {
+            if (lead) {
+              tc::mbar_arrive_expect_tx(&b_full[bs], p.nslab * FT_SLAB_B);
+              for (int s = 0; s < p.nslab; ++s)
+                tc::tma_load_2d(&map_genes, &b_full[bs], b_buf + (bs * p.nslab + s) * FT_SLAB_B, s * 64, (gt0 + g) * FT_GENES);
+            }
+            if (++bs == NB) { bs = 0; bph ^= 1; }
+          }
         }
       }
-    }
-  } else if (warp == FT_W_Y) {
-    FT_REGS_PRODUCER();
-    if (lane == 0) {
+    } else if (warp == FT_W_Y && act) {
       // ===== TMA producer of the count tiles (HBM): runs y_stages tiles ahead of the epilogue,
       // independent of the MMA pipeline (ncu: the epilogue spent 10 % of its samples waiting for Y
       // while these loads were queued behind the factor ring) =====
@@ -219,71 +232,66 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
         int ct, gt0, ngt;
         unit_info(unit, ct, gt0, ngt);
         for (int g = 0; g < ngt; ++g) {
-          tc::mbar_wait_relaxed(&y_empty[ys], yph ^ 1, p.ns_prod);
-          // f_i rides along with the count tile (single batch): the 80 KB vector does not survive in the
-          // ~14 KB of L1 left beside 214 KB of shared memory, and an L2 round trip per chunk stalls the epilogue
-          tc::mbar_arrive_expect_tx(&y_full[ys], p.y_stage_bytes + (MB ? 0 : FT_GENES * 4));
-          tc::tma_load_2d(&map_y, &y_full[ys], y_buf + ys * p.y_stage_bytes, (gt0 + g) * FT_GENES, ct * FT_CELLS);
-          if (!MB) tc::bulk_load_1d(f_ring + ys * FT_GENES, p.f_row + (int64_t)(gt0 + g) * FT_GENES, FT_GENES * 4, &y_full[ys]);
+          pwait(&y_empty[ys], yph ^ 1, p.ns_prod, true);
+          if (lead) {
+            // f_i rides along with the count tile (single batch): the 80 KB vector does not survive in the
+            // ~14 KB of L1 left beside 214 KB of shared memory, and an L2 round trip per chunk stalls the epilogue
+            tc::mbar_arrive_expect_tx(&y_full[ys], p.y_stage_bytes + (MB ? 0 : FT_GENES * 4));
+            tc::tma_load_2d(&map_y, &y_full[ys], y_buf + ys * p.y_stage_bytes, (gt0 + g) * FT_GENES, ct * FT_CELLS);
+            if (!MB) tc::bulk_load_1d(f_ring + ys * FT_GENES, p.f_row + (int64_t)(gt0 + g) * FT_GENES, FT_GENES * 4, &y_full[ys]);
+          }
           if (++ys == (uint32_t)p.y_stages) { ys = 0; yph ^= 1; }
         }
       }
-    }
-  } else if (warp == 1) {
-    FT_REGS_PRODUCER();
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    } else if (warp == 1 && act) {
+      // ===== eta UMMA issuer =====
       constexpr uint32_t idesc = tc::instr_desc(0, 0, 0, 0, FT_CELLS, FT_GENES);
       uint32_t bs = 0, bph = 0, db = 0, aph = 0;
-      uint32_t dph[2] = {0, 0};
+      uint32_t dph = 0;
       for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
         int ct, gt0, ngt;
         unit_info(unit, ct, gt0, ngt);
-        tc::mbar_wait(a_full, aph);
+        pwait(a_full, aph, p.ns_mma, false);
         aph ^= 1;
         for (int g = 0; g < ngt; ++g) {
-          if (p.ns_mma) {
-            tc::mbar_wait_relaxed(&d_empty[db], dph[db] ^ 1, p.ns_mma);
-            tc::mbar_wait_relaxed(&b_full[bs], bph, p.ns_mma);
-          } else {
-            tc::mbar_wait(&d_empty[db], dph[db] ^ 1);
-            tc::mbar_wait(&b_full[bs], bph);
+          pwait(&d_empty[db], ((dph >> db) & 1u) ^ 1u, p.ns_mma, true);
+          pwait(&b_full[bs], bph, p.ns_mma, false);
+          if (lead) {
+            tc::fence_after_sync();
+            const uint32_t a0 = tc::smem_u32(a_buf), b0 = tc::smem_u32(b_buf + bs * p.nslab * FT_SLAB_B);
+            const uint32_t d = tmem_base + db * FT_GENES;
+            for (int k = 0; k < p.kk; ++k) {
+              const uint64_t da = tc::smem_desc_sw128(a0 + (k >> 2) * FT_SLAB_A + (k & 3) * 32, 16, 1024);
+              const uint64_t dbd = tc::smem_desc_sw128(b0 + (k >> 2) * FT_SLAB_B + (k & 3) * 32, 16, 1024);
+              tc::mma_f16(d, da, dbd, idesc, k > 0 ? 1u : 0u);
+            }
+            tc::mma_commit(&b_empty[bs]);
+            tc::mma_commit(&d_full[db]);
+            if (g == ngt - 1) tc::mma_commit(a_empty);
           }
-          tc::fence_after_sync();
-          const uint32_t a0 = tc::smem_u32(a_buf), b0 = tc::smem_u32(b_buf + bs * p.nslab * FT_SLAB_B);
-          const uint32_t d = tmem_base + db * FT_GENES;
-          for (int k = 0; k < p.kk; ++k) {
-            const uint64_t da = tc::smem_desc_sw128(a0 + (k >> 2) * FT_SLAB_A + (k & 3) * 32, 16, 1024);
-            const uint64_t dbd = tc::smem_desc_sw128(b0 + (k >> 2) * FT_SLAB_B + (k & 3) * 32, 16, 1024);
-            tc::mma_f16(d, da, dbd, idesc, k > 0 ? 1u : 0u);
-          }
-          tc::mma_commit(&b_empty[bs]);
-          tc::mma_commit(&d_full[db]);
-          if (g == ngt - 1) tc::mma_commit(a_empty);
-          dph[db] ^= 1; db ^= 1;
+          dph ^= 1u << db; db ^= 1;
           if (++bs == NB) { bs = 0; bph ^= 1; }
         }
       }
-    }
-  } else if (warp == FT_W_RETIRE) {
-    FT_REGS_PRODUCER();
-    if (lane == 0) {
+    } else if (warp == FT_W_RETIRE && act) {
       // ===== retire warp: ships each finished residual tile (TMA store; no CTA-wide barrier on this path)
       // and, PROD, feeds the same shared-memory tile to the product UMMAs =====
       constexpr uint32_t idesc_hi = tc::instr_desc(0, 0, 0, 0, FT_CELLS, 64);   // R_hi x [Q0_hi | Q0_lo]
       constexpr uint32_t idesc_lo = tc::instr_desc(0, 0, 0, 0, FT_CELLS, 32);   // R_lo x Q0_hi
       uint32_t rb = 0, ntile = 0;
-      uint32_t fph[2] = {0, 0};
+      uint32_t fph = 0;
       uint32_t pb = 0;
-      uint32_t peph[2] = {0, 0};
+      uint32_t peph = 0;
       for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
         int ct, gt0, ngt;
         unit_info(unit, ct, gt0, ngt);
         auto load_op = [&](uint32_t n, int gtile) {   // operand tile of global tile count n -> stage n % FT_NOP
           const uint32_t st = n % FT_NOP;
-          tc::mbar_wait_relaxed(&op_empty[st], ((n / FT_NOP) & 1u) ^ 1u, p.ns_prod);
-          tc::mbar_arrive_expect_tx(&op_full[st], FT_OP_BYTES);
-          tc::tma_load_2d(&map_op, &op_full[st], op_buf + st * FT_OP_BYTES, gtile * FT_GENES, 0);
+          pwait(&op_empty[st], ((n / FT_NOP) & 1u) ^ 1u, p.ns_prod, false);   // released by this warp's own commit
+          if (lead) {
+            tc::mbar_arrive_expect_tx(&op_full[st], FT_OP_BYTES);
+            tc::tma_load_2d(&map_op, &op_full[st], op_buf + st * FT_OP_BYTES, gtile * FT_GENES, 0);
+          }
         };
         if (PROD)
           for (int a = 0; a < FT_NOP - 1 && a < ngt; ++a) load_op(ntile + a, gt0 + a);
@@ -291,37 +299,42 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
           const int gene0 = (gt0 + g) * FT_GENES;
           // FT_NOP - 1 tiles ahead: that stage's last reader was issued one tile ago
           if (PROD && g + FT_NOP - 1 < ngt) load_op(ntile + FT_NOP - 1, gt0 + g + FT_NOP - 1);
-          tc::mbar_wait_relaxed(&r_full[rb], fph[rb], p.ns_prod);     // all 8 epilogue warps wrote (and proxy-fenced) their part
-          fph[rb] ^= 1;
+          pwait(&r_full[rb], (fph >> rb) & 1u, p.ns_prod, true);     // all 8 epilogue warps wrote (and proxy-fenced) their part
+          fph ^= 1u << rb;
           uint8_t* rt = r_buf + rb * FT_R_BYTES;
-          tc::tma_store_2d(&map_hi, rt, gene0, ct * FT_CELLS);
-          tc::tma_store_2d(&map_lo, rt + FT_CELLS * 128, gene0, ct * FT_CELLS);
-          tc::tma_store_commit();
-          tc::tma_store_wait_read<1>();                    // the previous tile's store has drained the other buffer
-          if (ntile >= 1) tc::mbar_arrive(&r_free[rb ^ 1]);
+          if (lead) {
+            tc::tma_store_2d(&map_hi, rt, gene0, ct * FT_CELLS);
+            tc::tma_store_2d(&map_lo, rt + FT_CELLS * 128, gene0, ct * FT_CELLS);
+            tc::tma_store_commit();
+            tc::tma_store_wait_read<1>();                    // the previous tile's store has drained the other buffer
+            if (ntile >= 1) tc::mbar_arrive(&r_free[rb ^ 1]);
+          }
           if (PROD) {
             const uint32_t st = ntile % FT_NOP;
-            if ((g & 1) == 0) { tc::mbar_wait(&p_empty[pb], peph[pb] ^ 1); peph[pb] ^= 1; }
-            tc::mbar_wait(&op_full[st], (ntile / FT_NOP) & 1u);
-            tc::fence_after_sync();
-            const uint32_t a_hi = tc::smem_u32(rt), a_lo = a_hi + FT_CELLS * 128, bt = tc::smem_u32(op_buf + st * FT_OP_BYTES);
-            const uint32_t d = tmem_base + 128 + pb * 64;
+            if ((g & 1) == 0) { pwait(&p_empty[pb], ((peph >> pb) & 1u) ^ 1u, 0, true); peph ^= 1u << pb; }
+            pwait(&op_full[st], (ntile / FT_NOP) & 1u, 0, false);
+            if (lead) {
+              tc::fence_after_sync();
+              const uint32_t a_hi = tc::smem_u32(rt), a_lo = a_hi + FT_CELLS * 128, bt = tc::smem_u32(op_buf + st * FT_OP_BYTES);
+              const uint32_t d = tmem_base + 128 + pb * 64;
 #pragma unroll
-            for (int ks = 0; ks < FT_GENES / 16; ++ks) {
-              const uint64_t da_hi = tc::smem_desc_sw128(a_hi + ks * 32, 16, 1024);
-              const uint64_t da_lo = tc::smem_desc_sw128(a_lo + ks * 32, 16, 1024);
-              const uint64_t dbd = tc::smem_desc_sw128(bt + ks * 32, 16, 1024);
-              tc::mma_f16(d, da_hi, dbd, idesc_hi, ((g & 1) || ks > 0) ? 1u : 0u);
-              tc::mma_f16(d, da_lo, dbd, idesc_lo, 1u);
+              for (int ks = 0; ks < FT_GENES / 16; ++ks) {
+                const uint64_t da_hi = tc::smem_desc_sw128(a_hi + ks * 32, 16, 1024);
+                const uint64_t da_lo = tc::smem_desc_sw128(a_lo + ks * 32, 16, 1024);
+                const uint64_t dbd = tc::smem_desc_sw128(bt + ks * 32, 16, 1024);
+                tc::mma_f16(d, da_hi, dbd, idesc_hi, ((g & 1) || ks > 0) ? 1u : 0u);
+                tc::mma_f16(d, da_lo, dbd, idesc_lo, 1u);
+              }
+              tc::mma_commit(&op_empty[st]);
+              tc::mma_commit(&r_free[rb]);
+              if ((g & 1) || g == ngt - 1) tc::mma_commit(&p_full[pb]);
             }
-            tc::mma_commit(&op_empty[st]);
-            tc::mma_commit(&r_free[rb]);
-            if ((g & 1) || g == ngt - 1) { tc::mma_commit(&p_full[pb]); pb ^= 1; }
+            if ((g & 1) || g == ngt - 1) pb ^= 1;
           }
           rb ^= 1;
         }
       }
-      tc::tma_store_wait<0>();
+      if (lead) tc::tma_store_wait<0>();
     }
   } else if (PROD && warp >= FT_W_DRAIN0) {
     // ===== PROD drain warps: thread = one cell; every pair of gene tiles the fp32 TMEM accumulator
@@ -333,15 +346,15 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
 #pragma unroll
     for (int k = 0; k < 32; ++k) acc[k] = 0.0;
     uint32_t pbuf = 0;
-    uint32_t pfph[2] = {0, 0};
+    uint32_t pfph = 0;
     const double sc = (double)__ldg(p.op_inv) / (double)p.rscale;
     for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
       int ct, gt0, ngt;
       unit_info(unit, ct, gt0, ngt);
       const int npair = (ngt + 1) >> 1;
       for (int pr = 0; pr < npair; ++pr) {
-        tc::mbar_wait_relaxed(&p_full[pbuf], pfph[pbuf], p.ns_drain);
-        pfph[pbuf] ^= 1;
+        tc::mbar_wait_relaxed(&p_full[pbuf], (pfph >> pbuf) & 1u, p.ns_drain);
+        pfph ^= 1u << pbuf;
         tc::fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 128 + pbuf * 64;
 #pragma unroll
@@ -388,7 +401,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
     double sw64 = 0.0, syl64 = 0.0;
     float mw = 0.0f;
     uint32_t ys = 0, yph = 0, db = 0, rb = 0;
-    uint32_t dph[2] = {0, 0}, rfph[2] = {0, 0};
+    uint32_t dph = 0, rfph = 0;   // phase bits per buffer (bit masks: indexed arrays would live in local memory)
     for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
       int ct, gt0, ngt;
       unit_info(unit, ct, gt0, ngt);
@@ -400,19 +413,22 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
       const int64_t boff = (MB && cell_ok) ? (int64_t)__ldg(p.batch + cell) * p.ldI : 0;
       for (int g = 0; g < ngt; ++g) {
         const int gene0 = (gt0 + g) * FT_GENES;
-        tc::mbar_wait(&d_full[db], dph[db]);
-        dph[db] ^= 1;
+        tc::mbar_wait(&d_full[db], (dph >> db) & 1u);
+        dph ^= 1u << db;
         tc::mbar_wait(&y_full[ys], yph);
         tc::fence_after_sync();
         const uint8_t* yt = y_buf + ys * p.y_stage_bytes;
         uint8_t* rt = r_buf + rb * FT_R_BYTES;
-        // issue every load of the tile's two chunks first (TMEM, Y from smem, f_i broadcast), wait once,
-        // hand the TMEM buffer back to the MMA warp, then do the arithmetic
+        // Without the rider: issue every load of the tile's two chunks first (TMEM, Y from smem, f_i broadcast),
+        // wait once, hand the TMEM buffer back to the MMA warp, then do the arithmetic (168 registers).
+        // With it the kernel launches 512 threads at 128 registers and ptxas keeps the epilogue near that
+        // figure whatever setmaxnreg grants, rematerialising addresses all over the front-loaded form (+30 %
+        // instructions); loading one chunk at a time needs ~40 registers less and measures 2.77 vs 3.14 ms
+        // per pass at 114k cells (without the rider the front-loaded form stays ahead, 2.62 vs 2.72 ms).
         uint32_t xr2[2][16];
         uint4 yv[2][2];
         float4 fv[2][4];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        auto issue_loads = [&](int c) {
           const int col = ch * 32 + c * 16;            // first gene of the chunk within the tile
           tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + db * FT_GENES + col, xr2[c]);
           if (sizeof(YT) == 2) {
@@ -427,13 +443,22 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
           for (int k = 0; k < 4; ++k)
             fv[c][k] = MB ? __ldg(reinterpret_cast<const float4*>(p.f_row + boff + gene0 + col) + k)
                           : *reinterpret_cast<const float4*>(f_ring + ys * FT_GENES + col + 4 * k);
+        };
+        constexpr bool SEQ = PROD;
+        if constexpr (!SEQ) {
+          issue_loads(0); issue_loads(1);
+          tc::tmem_wait_ld();
+          tc::fence_before_sync();
+          tc::mbar_arrive(&d_empty[db]);               // accumulator is in registers: the next MMA may overwrite it
         }
-        tc::tmem_wait_ld();
-        tc::fence_before_sync();
-        tc::mbar_arrive(&d_empty[db]);                 // accumulator is in registers: the next MMA may overwrite it
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const int col = ch * 32 + c * 16;
+          if constexpr (SEQ) {
+            issue_loads(c);
+            tc::tmem_wait_ld();
+            if (c == 1) { tc::fence_before_sync(); tc::mbar_arrive(&d_empty[db]); }
+          }
           uint32_t (&xr)[16] = xr2[c];
           float y[16];
           if (sizeof(YT) == 2) {
@@ -499,8 +524,8 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
             lp[k] = *reinterpret_cast<const uint32_t*>(&l2);
           }
           if (c == 0) {   // the store that read r_buf[rb] two tiles ago must have drained it
-            tc::mbar_wait(&r_free[rb], rfph[rb] ^ 1);
-            rfph[rb] ^= 1;
+            tc::mbar_wait(&r_free[rb], ((rfph >> rb) & 1u) ^ 1u);
+            rfph ^= 1u << rb;
           }
           const int q0 = col >> 3;
           uint8_t* rh = rt + row * 128;
@@ -636,14 +661,14 @@ rowsum_tc_kernel(const __grid_constant__ CUtensorMap map_genes, const __grid_con
     if (lane == 0) {
       constexpr uint32_t idesc = tc::instr_desc(0, 0, 0, 0, RT_TILE, RT_TILE);
       uint32_t bs = 0, bph = 0, db = 0, aph = 0;
-      uint32_t dph[2] = {0, 0};
+      uint32_t dph = 0;
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         int gt, ct0, nct;
         unit_info(unit, gt, ct0, nct);
         tc::mbar_wait(a_full, aph);
         aph ^= 1;
         for (int c = 0; c < nct; ++c) {
-          tc::mbar_wait(&d_empty[db], dph[db] ^ 1);
+          tc::mbar_wait(&d_empty[db], ((dph >> db) & 1u) ^ 1u);
           tc::mbar_wait(&b_full[bs], bph);
           tc::fence_after_sync();
           const uint32_t a0 = tc::smem_u32(a_buf), b0 = tc::smem_u32(b_buf + bs * p.nslab * RT_SLAB);
@@ -656,7 +681,7 @@ rowsum_tc_kernel(const __grid_constant__ CUtensorMap map_genes, const __grid_con
           tc::mma_commit(&b_empty[bs]);
           tc::mma_commit(&d_full[db]);
           if (c == nct - 1) tc::mma_commit(a_empty);
-          dph[db] ^= 1; db ^= 1;
+          dph ^= 1u << db; db ^= 1;
           if (++bs == 2) { bs = 0; bph ^= 1; }
         }
       }
@@ -668,7 +693,7 @@ rowsum_tc_kernel(const __grid_constant__ CUtensorMap map_genes, const __grid_con
     const float L_hi = 1.4426950216293335f * inv, L_lo = 1.9259629911e-08f * inv;
     const float clampv = 8.0f / inv;
     uint32_t db = 0;
-    uint32_t dph[2] = {0, 0};
+    uint32_t dph = 0;
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
       int gt, ct0, nct;
       unit_info(unit, gt, ct0, nct);
@@ -680,8 +705,8 @@ rowsum_tc_kernel(const __grid_constant__ CUtensorMap map_genes, const __grid_con
       }
       for (int c = 0; c < nct; ++c) {
         const float* gp = p.g_col + (int64_t)(ct0 + c) * RT_TILE + ch * 32;
-        tc::mbar_wait(&d_full[db], dph[db]);
-        dph[db] ^= 1;
+        tc::mbar_wait(&d_full[db], (dph >> db) & 1u);
+        dph ^= 1u << db;
         tc::fence_after_sync();
         float ts = 0.0f;
 #pragma unroll
