@@ -328,7 +328,31 @@ def test_fused_product_rider_matches_plain_pass(I, J, d, M, kw, gen, monkeypatch
     assert rider["_prof"]["svd_passes"] < plain["_prof"]["svd_passes"]          # the rider really ran
     n = min(len(plain["_LL"]), len(rider["_LL"]))
     np.testing.assert_array_equal(plain["_accepted"][:n], rider["_accepted"][:n])
-    np.testing.assert_allclose(rider["_LL"][:n], plain["_LL"][:n], rtol=1e-9)
-    np.testing.assert_allclose(rider["alpha"], plain["alpha"], atol=1e-7)
-    assert principal_angle(rider["U"], plain["U"]) < 1e-5
+    np.testing.assert_array_equal(rider["_LL"][:n], plain["_LL"][:n])     # bit-identical: see eta_tc.cu PROD
+    np.testing.assert_array_equal(rider["alpha"], plain["alpha"])
+    assert principal_angle(rider["U"], plain["U"]) < 1e-12
     assert assert_fit_parity(o_gbm_sc(Y, M, **kw), rider) in ("full", "knife-edge")
+
+
+@pytest.mark.parametrize("variant", ["batches", "u8"])
+def test_fused_product_rider_other_instantiations(variant, monkeypatch):
+    """The rider's multi-batch and u8-count instantiations; the whole fit is bit-identical with and without it
+    (the rider's R^T Q0 equals prod_t's bit for bit, and c * (2^k acc) rounds like (c 2^k) * acc)."""
+    from scgbm_b200 import gbm_sc
+    rng = np.random.default_rng(11)
+    Y = _sim(300, 700, 5, seed=21)
+    kw = dict(max_iter=20)
+    if variant == "batches":
+        Y = Y + 1 * (rng.random(Y.shape) < 0.2)
+        kw["batch"] = rng.choice(np.array(["x", "y"]), size=Y.shape[1])
+    else:
+        Y = np.minimum(Y, 200)
+        kw["y_storage"] = 1        # SCGBM_STORE_U8
+    monkeypatch.setenv("SCGBM_FUSED_PROD", "0")
+    plain = gbm_sc(Y, 5, diagnostics=True, **kw)
+    monkeypatch.setenv("SCGBM_FUSED_PROD", "force")
+    rider = gbm_sc(Y, 5, diagnostics=True, **kw)
+    assert rider["_prof"]["svd_passes"] < plain["_prof"]["svd_passes"]
+    np.testing.assert_array_equal(rider["_LL"], plain["_LL"])
+    np.testing.assert_array_equal(rider["U"], plain["U"])
+    np.testing.assert_array_equal(rider["V"], plain["V"])

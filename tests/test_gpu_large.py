@@ -50,5 +50,5 @@ def test_large_fit_with_product_rider(monkeypatch):
     np.testing.assert_array_equal(a["_LL"], b["_LL"])
     np.testing.assert_array_equal(a["U"], b["U"])
     np.testing.assert_array_equal(a["_accepted"], plain["_accepted"])
-    np.testing.assert_allclose(a["_LL"], plain["_LL"], rtol=1e-9)
-    np.testing.assert_allclose(a["alpha"], plain["alpha"], atol=1e-7)
+    np.testing.assert_array_equal(a["_LL"], plain["_LL"])       # the rider is bit-identical to the plain first pass
+    np.testing.assert_array_equal(a["alpha"], plain["alpha"])
