@@ -304,10 +304,12 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                "kernel": "fused_tc_kernel<uint16_t> (K4 fused likelihood pass: tcgen05 eta tile, TMA in/out)",
+                "kernel": "fused_tc_kernel<uint16_t> (K4 fused likelihood pass: tcgen05 eta tile, TMA in/out; on shards "
+                          "of >= 4 cell tiles per SM the launch also carries the SVD's first product R^T Q0, which "
+                          "adds no algorithmic HBM bytes and replaces one 4N-byte pass of prod_tc_kernel)",
                 "peak_source": peak_src, "bytes_per_launch": fused_bytes, "ms_per_launch": fused_ms,
-                "traffic_note": "ncu dram bytes of the same kernel on a 20000x100000 shard (profiles/fused_traffic.json): "
-                                "1.012x its algorithmic bytes; scales with the shard",
+                "traffic_note": "ncu dram bytes of the same kernel on a 20000x100000 shard (profiles/fused_traffic.json, "
+                                "profiles/r01h_kernels.md): 1.005x its algorithmic bytes; scales with the shard",
                 "note": "algorithmic bytes = N*s_Y + 4N (two fp16 residual planes) + 4M(I+J) + 8(I+J), this rank's shard"}
     value = K / (ms * 1e-3)
 
