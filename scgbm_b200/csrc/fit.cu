@@ -101,31 +101,68 @@ __global__ void stage_factor_kernel(int64_t n_real, int64_t ld, int M, const dou
 // MAXONLY: only max |z| (as float bits, non-negative floats order like ints) -> zmax;
 // otherwise the fp16 planes of scale * z.
 template <typename YT, bool MAXONLY>
-__global__ void init_z_kernel(int64_t I, int64_t ldI, int64_t J, const YT* __restrict__ Y,
-                              const float* __restrict__ s_row /* ldI x nbatch */, const float* __restrict__ t_col,
-                              const int32_t* __restrict__ batch, float scale, uint16_t* __restrict__ Zhi,
-                              uint16_t* __restrict__ Zlo, int* __restrict__ zmax) {
-  const int64_t j = blockIdx.y;
-  const int kb = batch ? batch[j] : 0;
-  const float tj = t_col[j];
+__global__ void __launch_bounds__(256)
+init_z_kernel(int64_t I, int64_t ldI, int64_t J, const YT* __restrict__ Y,
+              const float* __restrict__ s_row /* ldI x nbatch */, const float* __restrict__ t_col,
+              const int32_t* __restrict__ batch, float scale, uint16_t* __restrict__ Zhi,
+              uint16_t* __restrict__ Zlo, int* __restrict__ zmax) {
+  // one column (cell) per block trip, 8 consecutive genes per thread trip (ldI is a multiple of 64)
   float m = 0.0f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ldI; i += (int64_t)gridDim.x * blockDim.x) {
-    float z = 0.0f;
-    if (i < I) {
-      const float st = s_row[(int64_t)kb * ldI + i] * tj;
-      z = (float)Y[j * ldI + i] * st - 1.0f / st;
-    }
-    if (MAXONLY) {
-      m = fmaxf(m, fabsf(z));
-    } else {
-      uint16_t h, l;
-      split_f16x2(z * scale, h, l);
-      Zhi[j * ldI + i] = h; Zlo[j * ldI + i] = l;
+  for (int64_t j = blockIdx.x; j < J; j += gridDim.x) {
+    const int kb = batch ? batch[j] : 0;
+    const float tj = t_col[j];
+    const YT* yc = Y + j * ldI;
+    const float* sr = s_row + (int64_t)kb * ldI;
+    for (int64_t i0 = (int64_t)threadIdx.x * 8; i0 < ldI; i0 += (int64_t)blockDim.x * 8) {
+      float y[8];
+      if (sizeof(YT) == 1) {
+        const uint2 v = *reinterpret_cast<const uint2*>(yc + i0);
+        const uint32_t w[2] = {v.x, v.y};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[k] = (float)((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+      } else if (sizeof(YT) == 2) {
+        const uint4 v = *reinterpret_cast<const uint4*>(yc + i0);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[k] = (float)((w[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[k] = (float)yc[i0 + k];
+      }
+      const float4 s0 = *reinterpret_cast<const float4*>(sr + i0), s1 = *reinterpret_cast<const float4*>(sr + i0 + 4);
+      const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      uint32_t hp[4], lp[4];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float z = 0.0f;
+        if (i0 + k < I) {
+          const float st = sv[k] * tj;
+          z = y[k] * st - 1.0f / st;
+        }
+        if (MAXONLY) {
+          m = fmaxf(m, fabsf(z));
+        } else {
+          uint16_t h, l;
+          split_f16x2(z * scale, h, l);
+          if (k & 1) { hp[k >> 1] |= (uint32_t)h << 16; lp[k >> 1] |= (uint32_t)l << 16; }
+          else { hp[k >> 1] = h; lp[k >> 1] = l; }
+        }
+      }
+      if (!MAXONLY) {
+        *reinterpret_cast<uint4*>(Zhi + j * ldI + i0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        *reinterpret_cast<uint4*>(Zlo + j * ldI + i0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+      }
     }
   }
-  if (MAXONLY) {
+  if (MAXONLY) {   // one atomic per block (a per-warp atomic on a single address serialised the whole pass)
+    __shared__ float red[8];
     m = warp_max(m);
-    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(zmax, __float_as_int(m));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+      if (m > 0.0f) atomicMax(zmax, __float_as_int(m));
+    }
   }
 }
 
@@ -330,19 +367,14 @@ struct FitState {
 
   template <bool MAXONLY>
   void launch_init_z(float scale, int* zmax) {
-    dim3 grid((unsigned)std::min<int64_t>(ceil_div(ldI, 256), 64), 1);
-    const int64_t slab = 65535;
-    for (int64_t j0 = 0; j0 < J; j0 += slab) {
-      grid.y = (unsigned)std::min(slab, J - j0);
-      const int32_t* bt = Y.batch.get() ? Y.batch.get() + j0 : nullptr;
-      uint16_t* zh = Rhi.get() + j0 * ldI; uint16_t* zl = Rlo.get() + j0 * ldI;
-      switch (Y.storage) {
-        case SCGBM_STORE_U8: init_z_kernel<uint8_t, MAXONLY><<<grid, 256, 0, ctx.stream>>>(I, ldI, J - j0, (const uint8_t*)Y.data + j0 * ldI, s_row.get(), t_col.get() + j0, bt, scale, zh, zl, zmax); break;
-        case SCGBM_STORE_U16: init_z_kernel<uint16_t, MAXONLY><<<grid, 256, 0, ctx.stream>>>(I, ldI, J - j0, (const uint16_t*)Y.data + j0 * ldI, s_row.get(), t_col.get() + j0, bt, scale, zh, zl, zmax); break;
-        default: init_z_kernel<float, MAXONLY><<<grid, 256, 0, ctx.stream>>>(I, ldI, J - j0, (const float*)Y.data + j0 * ldI, s_row.get(), t_col.get() + j0, bt, scale, zh, zl, zmax); break;
-      }
-      SCGBM_LAUNCH_CHECK();
+    const unsigned grid = (unsigned)std::min<int64_t>(J, (int64_t)ctx.num_sms * 16);
+    const int32_t* bt = Y.batch.get();
+    switch (Y.storage) {
+      case SCGBM_STORE_U8: init_z_kernel<uint8_t, MAXONLY><<<grid, 256, 0, ctx.stream>>>(I, ldI, J, (const uint8_t*)Y.data, s_row.get(), t_col.get(), bt, scale, Rhi.get(), Rlo.get(), zmax); break;
+      case SCGBM_STORE_U16: init_z_kernel<uint16_t, MAXONLY><<<grid, 256, 0, ctx.stream>>>(I, ldI, J, (const uint16_t*)Y.data, s_row.get(), t_col.get(), bt, scale, Rhi.get(), Rlo.get(), zmax); break;
+      default: init_z_kernel<float, MAXONLY><<<grid, 256, 0, ctx.stream>>>(I, ldI, J, (const float*)Y.data, s_row.get(), t_col.get(), bt, scale, Rhi.get(), Rlo.get(), zmax); break;
     }
+    SCGBM_LAUNCH_CHECK();
   }
 
   void init_svd() {
