@@ -13,8 +13,9 @@
 //     thread = one cell (TMEM lane), 16 consecutive genes per tcgen05.ld chunk; Y tile arrives
 //     by TMA (128B swizzle: a thread's 32-byte run per chunk is conflict-free), the two fp16
 //     planes of scale*(Y - W) leave by TMA store from a double-buffered smem tile.  Twelve warps:
-//     factor-operand TMA, UMMA issue, 8 x epilogue, residual TMA store, count-tile TMA; every
-//     hand-off is an mbarrier.
+//     factor-operand TMA, UMMA issue, retire (residual TMA store), count-tile TMA, 8 x epilogue;
+//     every hand-off is an mbarrier.  The PROD instantiation (product rider, see the kernel) also
+//     multiplies each outgoing residual tile with the SVD's start block and adds four drain warps.
 //     sum W, sum_nz Y*x, max W are reduced fp32 per chunk -> fp64 per thread -> CTA partial;
 //     sum_nz Y log W = sum Y*x + sum_i alpha_i rs_i + sum_j beta_j cs_j (+ clip correction).
 //   rowsum_tc_kernel (K3, R/fit.R:127-130): D[128 genes x 128 cells]; epilogue thread = one
