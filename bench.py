@@ -222,9 +222,13 @@ def main():
     comm = None
     dist = None
     if world > 1:
-        # stdout must carry exactly one JSON line: NCCL_DEBUG=VERSION would print a banner there
+        # stdout must carry exactly one JSON line.  NCCL prints its "NCCL version ..." banner there at every level
+        # from VERSION up (WARN included), and a level can also come from /etc/nccl.conf: an explicit value NCCL
+        # does not know ("NONE") switches the banner off; a level the user asked for is sent to stderr instead.
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+            os.environ["NCCL_DEBUG"] = "NONE"
+        elif "NCCL_DEBUG_FILE" not in os.environ:
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         import torch
         import torch.distributed as dist
         dist.init_process_group("gloo", rank=rank, world_size=world)
