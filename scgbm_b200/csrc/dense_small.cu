@@ -9,63 +9,66 @@ namespace scgbm {
 
 // ---------------------------------------------------------------------------------
 // ts_gram:  C[p x q] = alpha * A^T B,   A: n x p (lda), B: n x q (ldb), n large.
-// Stage 1: grid (chunks, p/64, q/64); each CTA reduces its row chunk into a 64x64
+// Stage 1: grid (chunks, p/PT, q/QT); each CTA reduces its row chunk into a PT x QT
 // block of partial[chunk] (fp64).  Stage 2 sums the chunks in a fixed order.
 // ---------------------------------------------------------------------------------
 constexpr int GR_TB = 64;     // output block edge
 constexpr int GR_KS = 32;     // rows per smem slab
 constexpr int GR_NT = 256;    // threads: 16 x 16, each 4 x 4 outputs
 
+// PT x QT output block (64 or 32 each): the Krylov blocks are 32 wide at M = 20, so a fixed 64 x 64 block
+// would spend half (q = 32) to 85 % (p = 20, q = 32) of its fp64 FMAs on zero padding.
+template <int PT, int QT>
 __global__ void __launch_bounds__(GR_NT)
 ts_gram_partial(int64_t n, int p, int q, const double* __restrict__ A, int64_t lda,
                 const double* __restrict__ B, int64_t ldb, double* __restrict__ part,
                 int64_t rows_per_chunk) {
-  __shared__ double As[GR_KS][GR_TB + 1];
-  __shared__ double Bs[GR_KS][GR_TB + 1];
+  constexpr int NA = PT / 16, NB = QT / 16;
+  __shared__ double As[GR_KS][PT + 1];
+  __shared__ double Bs[GR_KS][QT + 1];
   const int chunk = blockIdx.x;
-  const int p0 = blockIdx.y * GR_TB, q0 = blockIdx.z * GR_TB;
+  const int p0 = blockIdx.y * PT, q0 = blockIdx.z * QT;
   const int tp = threadIdx.x % 16, tq = threadIdx.x / 16;
   const int64_t r_begin = (int64_t)chunk * rows_per_chunk;
   const int64_t r_end = min(n, r_begin + rows_per_chunk);
-  double acc[4][4];
+  double acc[NA][NB];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < NA; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int b = 0; b < NB; ++b) acc[a][b] = 0.0;
 
   for (int64_t r0 = r_begin; r0 < r_end; r0 += GR_KS) {
-    // load slabs: GR_KS rows x 64 columns each; rows contiguous in global (col-major)
-    for (int idx = threadIdx.x; idx < GR_KS * GR_TB; idx += GR_NT) {
+    // load slabs: GR_KS rows x PT (QT) columns; rows contiguous in global (col-major)
+    for (int idx = threadIdx.x; idx < GR_KS * PT; idx += GR_NT) {
       const int rr = idx % GR_KS, cc = idx / GR_KS;
       const int64_t r = r0 + rr;
-      double va = 0.0, vb = 0.0;
-      if (r < r_end) {
-        if (p0 + cc < p) va = A[(int64_t)(p0 + cc) * lda + r];
-        if (q0 + cc < q) vb = B[(int64_t)(q0 + cc) * ldb + r];
-      }
-      As[rr][cc] = va;
-      Bs[rr][cc] = vb;
+      As[rr][cc] = (r < r_end && p0 + cc < p) ? A[(int64_t)(p0 + cc) * lda + r] : 0.0;
+    }
+    for (int idx = threadIdx.x; idx < GR_KS * QT; idx += GR_NT) {
+      const int rr = idx % GR_KS, cc = idx / GR_KS;
+      const int64_t r = r0 + rr;
+      Bs[rr][cc] = (r < r_end && q0 + cc < q) ? B[(int64_t)(q0 + cc) * ldb + r] : 0.0;
     }
     __syncthreads();
 #pragma unroll 4
     for (int k = 0; k < GR_KS; ++k) {
-      double av[4], bv[4];
+      double av[NA], bv[NB];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) av[a] = As[k][tp + 16 * a];
+      for (int a = 0; a < NA; ++a) av[a] = As[k][tp + 16 * a];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) bv[b] = Bs[k][tq + 16 * b];
+      for (int b = 0; b < NB; ++b) bv[b] = Bs[k][tq + 16 * b];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < NA; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+        for (int b = 0; b < NB; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
     }
     __syncthreads();
   }
   double* out = part + (int64_t)chunk * p * q;
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < NA; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < NB; ++b) {
       const int pi = p0 + tp + 16 * a, qi = q0 + tq + 16 * b;
       if (pi < p && qi < q) out[(int64_t)qi * p + pi] = acc[a][b];
     }
@@ -91,15 +94,18 @@ void ts_gram(Ctx& ctx, SmallWs& ws, int64_t n, int p, int q, const double* A, in
              const double* B, int64_t ldb, double* C, int ldc, double alpha, double beta) {
   if (p <= 0 || q <= 0) return;
   // enough chunks to fill the machine twice over, at least two smem slabs each
-  const int64_t blocks_pq = ceil_div(p, GR_TB) * ceil_div(q, GR_TB);
+  const int PT = p <= 32 ? 32 : GR_TB, QT = q <= 32 ? 32 : GR_TB;
+  const int64_t blocks_pq = ceil_div(p, PT) * ceil_div(q, QT);
   const int64_t want_chunks = std::max<int64_t>(1, ceil_div((int64_t)ctx.num_sms * 2, blocks_pq));
   int64_t rows_per_chunk = std::max<int64_t>(2 * GR_KS, round_up(ceil_div(n, want_chunks), GR_KS));
   int nchunk = (int)std::max<int64_t>(1, ceil_div(n, rows_per_chunk));
   ws.need_partial((int64_t)nchunk * p * q);
   ProfScope ps(ctx.prof, SCGBM_K_SMALL, 2);
-  dim3 grid(nchunk, (unsigned)ceil_div(p, GR_TB), (unsigned)ceil_div(q, GR_TB));
-  ts_gram_partial<<<grid, GR_NT, 0, ctx.stream>>>(n, p, q, A, lda, B, ldb, ws.partial.get(),
-                                                  rows_per_chunk);
+  dim3 grid(nchunk, (unsigned)ceil_div(p, PT), (unsigned)ceil_div(q, QT));
+  if (PT == 32 && QT == 32) ts_gram_partial<32, 32><<<grid, GR_NT, 0, ctx.stream>>>(n, p, q, A, lda, B, ldb, ws.partial.get(), rows_per_chunk);
+  else if (PT == 64 && QT == 32) ts_gram_partial<64, 32><<<grid, GR_NT, 0, ctx.stream>>>(n, p, q, A, lda, B, ldb, ws.partial.get(), rows_per_chunk);
+  else if (PT == 32 && QT == 64) ts_gram_partial<32, 64><<<grid, GR_NT, 0, ctx.stream>>>(n, p, q, A, lda, B, ldb, ws.partial.get(), rows_per_chunk);
+  else ts_gram_partial<64, 64><<<grid, GR_NT, 0, ctx.stream>>>(n, p, q, A, lda, B, ldb, ws.partial.get(), rows_per_chunk);
   SCGBM_LAUNCH_CHECK();
   ts_gram_reduce<<<(unsigned)ceil_div((int64_t)p * q * 32, 256), 256, 0, ctx.stream>>>(nchunk, p, q, ws.partial.get(),
                                                                         C, ldc, alpha, beta);
