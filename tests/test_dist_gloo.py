@@ -80,3 +80,87 @@ def test_shard_range_tiles(J, n):
         assert a[1] == b[0]
     sizes = [b - a for a, b in edges]
     assert max(sizes) - min(sizes) <= 1
+
+
+# ---------------------------------------------------------------------------------------------
+# Cell-sharded gbm.sc(subset=) (BASELINE configs[3]): the host logic of
+# scgbm_b200/projection.py -- subsample handling, row filter, the two all-reduces and the re-centring of
+# R/fit.R:272-277 -- on two gloo ranks.  The two GPU entry points it calls are stood in for by the oracle
+# (tests may do that; the product never does), so this runs without a device.
+# ---------------------------------------------------------------------------------------------
+def _proj_worker(rank, world, port, q):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import scgbm_b200.api as api
+    from scgbm_b200 import _lib as L
+    from scgbm_b200.dist import shard_range
+    from scgbm_b200.projection import gbm_proj_parallel
+    from oracle import scgbm_oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        Y = O.sim_data(60, 90, 2, seed=4)["Y"].astype(np.int32)
+        Y[5, :] = 0; Y[5, 1] = 3                       # a gene that the > 5 row filter (R/fit.R:225) drops
+        jxs = np.arange(0, 90, 2)
+        j0, j1 = shard_range(Y.shape[1], rank, world)
+
+        def fake_fit(Ysub, M, **kw):                   # stands in for scgbm_fit
+            return O.gbm_sc(np.asarray(Ysub, dtype=np.float64), M, tol=kw.get("tol", 1e-4), max_iter=kw.get("max_iter", 100))
+
+        def fake_project(a_ref, o_ref):                # stands in for scgbm_project (R/fit.R:248-264)
+            a, o = a_ref._obj, o_ref._obj
+            assert a.y_dtype == L.I32 and not a.y_on_device
+            J, Ik, M = a.J, a.Ik, a.M
+            Yl = np.ctypeslib.as_array(C.cast(a.Y, C.POINTER(C.c_int32)), shape=(J, a.ldY)).T.astype(np.float64)
+            ixs = np.ctypeslib.as_array(C.cast(a.ixs, C.POINTER(C.c_int64)), shape=(Ik,))
+            U = np.ctypeslib.as_array(C.cast(a.U, C.POINTER(C.c_double)), shape=(M, Ik)).T
+            alpha = np.ctypeslib.as_array(C.cast(a.alpha, C.POINTER(C.c_double)), shape=(Ik,))
+            beta = np.ctypeslib.as_array(C.cast(o.beta, C.POINTER(C.c_double)), shape=(J,))
+            sc = np.ctypeslib.as_array(C.cast(o.scores, C.POINTER(C.c_double)), shape=(M, J))
+            se = np.ctypeslib.as_array(C.cast(o.se_scores, C.POINTER(C.c_double)), shape=(M, J))
+            X = np.hstack([np.ones((Ik, 1)), U])
+            for j in range(J):
+                coef, s, _, _ = O.poisson_glm_irls(X, Yl[ixs, j], alpha)
+                beta[j] = coef[0]; sc[:, j] = coef[1:]; se[:, j] = s[1:]
+            return 0
+
+        class GlooComm:                                # the two collectives Comm offers, over gloo
+            handle = None
+
+            def allreduce(self, arr, op="sum"):
+                t = torch.tensor(np.ascontiguousarray(arr, dtype=np.float64))
+                dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+                return t.numpy()
+
+        api.gbm_sc = fake_fit
+        L.load().scgbm_project = fake_project
+        out = gbm_proj_parallel(np.asfortranarray(Y[:, j0:j1]), 2, comm=GlooComm(),
+                                subsample_Y=np.asfortranarray(Y[:, jxs]), max_iter=15)
+        q.put((rank, out["alpha"], out["beta"], out["scores"], out["se_scores"], out["U"], out["_ixs"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_projection_host_logic():
+    import torch.multiprocessing as mp
+    from oracle import scgbm_oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_proj_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps: p.start()
+    res = sorted([q.get(timeout=240) for _ in ps], key=lambda r: r[0])
+    for p in ps:
+        p.join(60); assert p.exitcode == 0
+    Y = O.sim_data(60, 90, 2, seed=4)["Y"].astype(np.int32)
+    Y[5, :] = 0; Y[5, 1] = 3
+    ref = O.gbm_proj_parallel(Y.astype(np.float64), 2, subsample=np.arange(0, 90, 2) + 1, max_iter=15)
+    assert 5 not in ref["_ixs"]
+    for r in res:                                       # replicated on every rank
+        np.testing.assert_array_equal(r[6], ref["_ixs"])
+        np.testing.assert_allclose(r[1], ref["alpha"], atol=1e-10)
+        np.testing.assert_allclose(r[5], ref["U"], atol=1e-12)
+    np.testing.assert_allclose(np.concatenate([res[0][2], res[1][2]]), ref["beta"], atol=1e-10)
+    np.testing.assert_allclose(np.vstack([res[0][3], res[1][3]]), ref["scores"], atol=1e-10)
+    np.testing.assert_allclose(np.vstack([res[0][4], res[1][4]]), ref["se_scores"], rtol=1e-9)
