@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SCGBM_VERSION 100
+#define SCGBM_VERSION 200
 
 /* element type of a count matrix handed to the library */
 enum scgbm_dtype {
@@ -119,6 +119,12 @@ typedef struct scgbm_fit_args {
   const int64_t* csc_p; /* J + 1 column pointers            (dgCMatrix@p widened to 64 bit)     */
   const void*    csc_x; /* nnz values                       (dgCMatrix@x: SCGBM_F64)            */
   int32_t  csc_x_dtype; /* scgbm_dtype of csc_x                                                 */
+  /* --- multi-GPU from ONE caller (the reference's only calling convention is a single R session calling
+   * gbm.sc(), R/fit.R:52): ngpu >= 2 splits the cells over ngpu GPUs inside the library -- one host thread and
+   * one NCCL rank per GPU, rank 0 on the calling thread (so `progress` still fires there).  Y must be in host
+   * memory; every output buffer covers ALL cells.  Mutually exclusive with `comm` (one process per GPU). --- */
+  int32_t  ngpu;           /* 0 / 1: single GPU                                                 */
+  const int32_t* devices;  /* ngpu CUDA ordinals, or NULL: device, device + 1, ...              */
 } scgbm_fit_args;
 
 typedef struct scgbm_fit_out {
@@ -149,6 +155,13 @@ typedef struct scgbm_fit_out {
   double* Xu;     /* I x M */
   double* Xv;     /* J x M */
   int32_t x_rank;
+  /* diagnostics of the truncated SVD that stands in for irlba (R/fit.R:115,323): irlba iterates to maxit and
+   * warns; here the cycle budget is fixed, so calls that returned with a Ritz residual estimate >= svd_tol
+   * are counted (the wrappers turn a non-zero count into a warning) */
+  int32_t svd_unconverged;
+  int32_t underflow_reruns; /* iterations re-evaluated on the CUDA-core pass because exp(eta) could underflow
+                             * in the reference's doubles (log(0) = -Inf branch, R/fit.R:152-157)            */
+  double  svd_worst_est;
 } scgbm_fit_out;
 
 int scgbm_fit(const scgbm_fit_args* args, scgbm_fit_out* out);
@@ -184,6 +197,8 @@ typedef struct scgbm_se_args {
   int32_t device;
   scgbm_comm* comm;
   int32_t profile;
+  int32_t ngpu;            /* >= 2: cells split over ngpu GPUs inside the library (as in scgbm_fit_args) */
+  const int32_t* devices;
 } scgbm_se_args;
 
 typedef struct scgbm_se_out {

@@ -101,9 +101,10 @@ def process_results(out):
 
 def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False,
            return_W=True, batch=None, time_by_iter=False, min_iter=30,
-           svd="exact", rng=None, verbose=False):
+           svd="exact", rng=None, verbose=False, _ll_inject=None):
     """R/fit.R:52-211.  `batch` is an int array of 1-based codes (as.integer of
-    the factor, :90) or None for a single batch."""
+    the factor, :90) or None for a single batch.  `_ll_inject` ({iteration: value}, test hook) replaces the
+    objective of those iterations, to drive the NaN/Inf branch of :152-157 (quirks Q1, Q2) at will."""
     Y = np.asarray(Y, dtype=np.float64)
     check_valid_input(Y, M)                                            # :65
     if subset is not None:                                             # :67-73
@@ -168,6 +169,8 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
                 t0 = t1
             W[W > max_Y] = max_Y                                       # :145
             LL[i - 1] = (Y[nz] * np.log(W[nz])).sum() - W.sum()        # :151
+            if _ll_inject and i in _ll_inject:
+                LL[i - 1] = _ll_inject[i]
         lr_trace.append(lr)
         if math.isnan(LL[i - 1]) or math.isinf(LL[i - 1]):             # :152-157
             X = Xt

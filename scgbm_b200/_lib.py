@@ -52,7 +52,8 @@ class FitArgs(C.Structure):
                 ("svd_extra", C.c_int32), ("svd_depth", C.c_int32), ("svd_tol", C.c_double),
                 ("seed", C.c_uint64), ("profile", C.c_int32), ("verbose", C.c_int32),
                 ("progress", PROGRESS_CB), ("progress_user", C.c_void_p),
-                ("csc_i", C.c_void_p), ("csc_p", C.c_void_p), ("csc_x", C.c_void_p), ("csc_x_dtype", C.c_int32)]
+                ("csc_i", C.c_void_p), ("csc_p", C.c_void_p), ("csc_x", C.c_void_p), ("csc_x_dtype", C.c_int32),
+                ("ngpu", C.c_int32), ("devices", C.c_void_p)]
 
 
 class FitOut(C.Structure):
@@ -62,7 +63,8 @@ class FitOut(C.Structure):
                 ("LL", C.c_void_p), ("accepted", C.c_void_p),
                 ("n_obj", C.c_int32), ("n_iter", C.c_int32), ("hit_max_iter", C.c_int32),
                 ("y_storage", C.c_int32), ("max_Y", C.c_double), ("prof", Profile),
-                ("Xu", C.c_void_p), ("Xv", C.c_void_p), ("x_rank", C.c_int32)]
+                ("Xu", C.c_void_p), ("Xv", C.c_void_p), ("x_rank", C.c_int32),
+                ("svd_unconverged", C.c_int32), ("underflow_reruns", C.c_int32), ("svd_worst_est", C.c_double)]
 
 
 class SeArgs(C.Structure):
@@ -70,7 +72,8 @@ class SeArgs(C.Structure):
                 ("U", C.c_void_p), ("scores", C.c_void_p), ("W", C.c_void_p),
                 ("alpha", C.c_void_p), ("beta", C.c_void_p), ("batch", C.c_void_p),
                 ("nbatch", C.c_int32), ("Xu", C.c_void_p), ("Xv", C.c_void_p), ("Mx", C.c_int32),
-                ("EPS", C.c_double), ("device", C.c_int32), ("comm", C.c_void_p), ("profile", C.c_int32)]
+                ("EPS", C.c_double), ("device", C.c_int32), ("comm", C.c_void_p), ("profile", C.c_int32),
+                ("ngpu", C.c_int32), ("devices", C.c_void_p)]
 
 
 class SeOut(C.Structure):

@@ -50,24 +50,60 @@ def _is_sparse(Y):
         return False
 
 
-def _batch_codes(batch, J):
+def _batch_codes(batch, J, comm=None, levels=None):
     """R: `batch` must be a factor (R/fit.R:86-88); here: any 1-D array of labels.
-    Returns 1-based int32 codes in order of first appearance of the SORTED levels
-    (as.integer(factor(x)))."""
+    Returns 1-based int32 codes = as.integer(factor(x, levels = sorted unique labels)) and the level count.
+
+    With `comm` (cells sharded over ranks) the levels are the union over ALL ranks: a shard that lacks a level
+    must still give its cells the same code as everybody else (include/scgbm.h: codes are globally consistent),
+    otherwise row sums, log.rsy and alpha[, batch] silently mix batches.  The union is agreed over the
+    library's own transport (Comm.allgather_bytes); explicit `levels` skip the exchange."""
     if batch is None:
+        if comm is not None:      # all ranks must agree that there is no batch argument
+            flags = comm.allgather_bytes(b"0")
+            if any(f != b"0" for f in flags):
+                raise RError(1, "batch must be given on every rank or on none")
         return None, 1
     b = np.asarray(batch)
     if b.shape != (J,):
         raise RError(1, "Batch must be encoded as factor.")
-    levels, codes = np.unique(b, return_inverse=True)
+    if levels is None:
+        levels = np.unique(b)
+        if comm is not None:
+            import pickle
+            parts = comm.allgather_bytes(b"1" + pickle.dumps(levels))
+            if any(p[:1] != b"1" for p in parts):
+                raise RError(1, "batch must be given on every rank or on none")
+            try:
+                levels = np.unique(np.concatenate([pickle.loads(p[1:]) for p in parts]))
+            except Exception as e:       # labels of different types on different ranks
+                raise RError(1, f"batch levels cannot be agreed across ranks: {e}")
+    else:
+        levels = np.unique(np.asarray(levels))
+    codes = np.searchsorted(levels, b)
+    ok = (codes < len(levels))
+    ok[ok] &= levels[codes[ok]] == b[ok]
+    if not ok.all():
+        raise RError(1, "batch contains labels that are not among the levels")
     return np.ascontiguousarray(codes.astype(np.int32) + 1), int(len(levels))
+
+
+def _canonical_csc(Y):
+    """dgCMatrix semantics for scipy input: duplicate (i, j) entries are SUMMED (Matrix and scipy both do) and
+    row indices sorted.  The scatter kernel writes entries, it does not add them, so duplicates must not reach
+    it (a last-writer-wins race would silently lose counts)."""
+    Ys = Y.tocsc()
+    if not Ys.has_canonical_format:
+        Ys = Ys.copy()
+        Ys.sum_duplicates()
+    return Ys
 
 
 def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False, return_W=True,
            batch=None, time_by_iter=False, min_iter=30, *, device=-1, comm=None, y_storage=L.STORE_AUTO,
            svd_extra=0, svd_depth=0, svd_tol=0.0, seed=0, profile=False, verbose=False, quiet=True,
            diagnostics=False, y_device_ptr=None, y_device_shape=None, y_device_dtype=None, rng=None,
-           keep_factors=False, subset_Y=None):
+           keep_factors=False, subset_Y=None, ngpu=1, devices=None, batch_levels=None):
     """gbm.sc(Y, M, max.iter, tol, subset, ncores, infer.beta, return.W, batch,
     time.by.iter, min.iter)   -- R/fit.R:52-62.
 
@@ -76,7 +112,9 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
     (adds `_LL`, `_accepted`, `_n_iter`, `_prof`), `y_device_ptr` (Y already
     resident in HBM in the library's own layout), `keep_factors` (adds `_Xu`, `_Xv`,
     `_batch`: the factors of the X that alpha/beta/W belong to, so that `get_se` works
-    after `return_W=False` -- the reference cannot, quirk Q9).
+    after `return_W=False` -- the reference cannot, quirk Q9), `ngpu` (>= 2: ONE call uses that many GPUs of
+    the box -- the library splits the cells over one host thread / NCCL rank per GPU; all outputs cover all
+    cells), `batch_levels` (explicit factor levels; with `comm` they are otherwise agreed across ranks).
     """
     if subset is not None or subset_Y is not None:             # R/fit.R:67-73
         from .projection import gbm_proj_parallel
@@ -91,7 +129,7 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
     csc = None
     if _is_sparse(Y):
         # Matrix::dgCMatrix-style input: handed over column-compressed, densified on the GPU
-        Ys = Y.tocsc()
+        Ys = _canonical_csc(Y)
         I, J = Ys.shape
         xs = np.ascontiguousarray(Ys.data)
         if xs.dtype not in _NP2DT:
@@ -109,9 +147,13 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
     if M < 1:
         raise RError(1, "M must be >= 1")                      # R/fit.R:296-298
     M = int(M)
-    codes, nbatch = _batch_codes(batch, J)
-    if comm is not None and codes is not None:
-        nbatch = int(comm.allreduce_max_int(nbatch))
+    codes, nbatch = _batch_codes(batch, J, comm=comm, levels=batch_levels)
+    ngpu = int(ngpu or 1)
+    if ngpu > 1 and (comm is not None or y_device_ptr is not None):
+        raise RError(1, "ngpu > 1 needs Y in host memory and no comm (comm = one process per GPU)")
+    dev_list = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+    if dev_list is not None and len(dev_list) != ngpu:
+        raise RError(1, "devices must list ngpu CUDA ordinals")
     max_iter = int(max_iter)
     U = np.zeros((I, M), order="F"); V = np.zeros((J, M), order="F"); D = np.zeros(M)
     loadings = np.zeros((I, M), order="F"); scores = np.zeros((J, M), order="F")
@@ -137,6 +179,7 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
     a.progress = cb; a.progress_user = None
     if csc is not None:
         a.csc_i = L.ptr(csc[0]); a.csc_p = L.ptr(csc[1]); a.csc_x = L.ptr(csc[2]); a.csc_x_dtype = y_dt
+    a.ngpu = ngpu; a.devices = L.ptr(dev_list)
     o = L.FitOut()
     o.U = L.ptr(U); o.D = L.ptr(D); o.V = L.ptr(V); o.loadings = L.ptr(loadings); o.scores = L.ptr(scores)
     o.alpha = L.ptr(alpha); o.beta = L.ptr(beta); o.obj = L.ptr(obj); o.time = L.ptr(tvec)
@@ -151,6 +194,9 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
     if o.hit_max_iter:                                          # R/fit.R:182-185
         warnings.warn("Maximum number of iterations reached (increase max.iter).\n"
                       "              Possible non-convergence.")
+    if o.svd_unconverged:                                       # irlba would warn "did not converge" [ext]
+        warnings.warn(f"truncated SVD: {o.svd_unconverged} call(s) returned with a residual estimate above svd_tol "
+                      f"(worst {o.svd_worst_est:.2e}); the projection of those iterations is approximate.")
     out = OrderedDict()                                         # element order: quirk Q13
     if return_W:
         out["W"] = W
@@ -176,10 +222,13 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
         out["_y_storage"] = int(o.y_storage)
         out["_max_Y"] = float(o.max_Y)
         out["_prof"] = o.prof.as_dict()
+        out["_svd_unconverged"] = int(o.svd_unconverged)
+        out["_svd_worst_est"] = float(o.svd_worst_est)
+        out["_underflow_reruns"] = int(o.underflow_reruns)
     return out
 
 
-def get_se(out, EPS=0.0, *, device=-1, comm=None, profile=False):
+def get_se(out, EPS=0.0, *, device=-1, comm=None, profile=False, ngpu=1, devices=None):
     """get.se(out, EPS)  -- R/uncertainty.R:14-35.  Needs out['W'] like the reference
     (quirk Q9), or -- extension -- the `keep_factors=True` outputs of gbm_sc, from which W is
     re-evaluated on the device chunk by chunk (the only option at sizes where W cannot exist)."""
@@ -208,6 +257,8 @@ def get_se(out, EPS=0.0, *, device=-1, comm=None, profile=False):
     a.I = I; a.J = J; a.M = M; a.U = L.ptr(U); a.scores = L.ptr(S)
     a.comm = comm.handle if comm is not None else None
     a.EPS = float(EPS); a.device = int(device); a.profile = int(bool(profile))
+    dev_list = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+    a.ngpu = int(ngpu or 1); a.devices = L.ptr(dev_list)
     o = L.SeOut()
     o.se_scores = L.ptr(se_s); o.se_loadings = L.ptr(se_l)
     st = lib.scgbm_get_se(C.byref(a), C.byref(o))

@@ -11,6 +11,8 @@ Comm* comm_create(const uint8_t* id, int nranks, int rank, int device);
 void comm_unique_id(uint8_t* id);
 void comm_destroy(Comm* c);
 void fit_impl(const scgbm_fit_args* a, scgbm_fit_out* out);
+void fit_multi_impl(const scgbm_fit_args* a, scgbm_fit_out* out);
+void get_se_multi_impl(const scgbm_se_args* a, scgbm_se_out* out);
 struct FitRun;
 FitRun* fit_begin_impl(const scgbm_fit_args* a);
 int fit_step_impl(FitRun* r, int n_steps);
@@ -56,7 +58,9 @@ static void use_device(int device) {
 
 extern "C" {
 
-int scgbm_fit(const scgbm_fit_args* args, scgbm_fit_out* out) { return guarded([&] { fit_impl(args, out); }); }
+int scgbm_fit(const scgbm_fit_args* args, scgbm_fit_out* out) {
+  return guarded([&] { if (args && args->ngpu > 1) fit_multi_impl(args, out); else fit_impl(args, out); });
+}
 int scgbm_fit_begin(const scgbm_fit_args* args, scgbm_fit_handle** h) {
   return guarded([&] { SCGBM_REQUIRE(h, "NULL handle pointer"); *h = reinterpret_cast<scgbm_fit_handle*>(fit_begin_impl(args)); });
 }
@@ -72,7 +76,9 @@ int scgbm_fit_set_profile(scgbm_fit_handle* h, int32_t level) {
 int scgbm_fit_end(scgbm_fit_handle* h, scgbm_fit_out* out) {
   return guarded([&] { fit_end_impl(reinterpret_cast<FitRun*>(h), out); });
 }
-int scgbm_get_se(const scgbm_se_args* args, scgbm_se_out* out) { return guarded([&] { get_se_impl(args, out); }); }
+int scgbm_get_se(const scgbm_se_args* args, scgbm_se_out* out) {
+  return guarded([&] { if (args && args->ngpu > 1) get_se_multi_impl(args, out); else get_se_impl(args, out); });
+}
 int scgbm_project(const scgbm_proj_args* args, scgbm_proj_out* out) { return guarded([&] { project_impl(args, out); }); }
 int scgbm_sim_counts(const scgbm_sim_args* args, void* Y_dev, int64_t* n_saturated) {
   return guarded([&] { SCGBM_REQUIRE(args && Y_dev, "NULL args"); sim_counts(args, Y_dev, n_saturated); });

@@ -66,6 +66,8 @@ void pass_rowsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, cons
 void pass_colsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* f_row, double* C);
 // alpha/beta (fp64) and this rank's row sums of Y close the objective:
 //   sum_nz Y log W = sum Y x + sum_i alpha_i rs_i + sum_j beta_j cs_j   (+ clip correction)
+// out3[3] = 1 flags an iteration in which exp(eta) may underflow in the reference's doubles (log(0) = -Inf for a
+// non-zero count, R/fit.R:152-157): the caller must then re-run it with pass_fused, which restates that.
 // Optional rider of the fused pass: out (J x b, column-major) = R^T Q0 for the residual this pass produces,
 // Q0 given as the two scaled fp16 planes prod_t would build ([hi 32 | lo 32][ldk]; products.cuh).
 struct FusedProd {

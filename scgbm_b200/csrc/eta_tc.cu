@@ -585,13 +585,20 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
 }
 
 // out[1] += sum_i alpha_i rs_i + sum_j beta_j cs_j   (single CTA, fp64, fixed order)
+// out[3]  = 1 when exp(eta) could underflow to 0 in the reference's doubles for some entry: R then has
+//           log(0) = -Inf for a non-zero count and takes the NaN/Inf branch (R/fit.R:152-157).  The tensor-core
+//           pass sums Y * eta directly and would never see that, so the caller re-runs such an iteration on the
+//           CUDA-core pass, which restates the underflow entry by entry (eta_pass.cu).  The test is a bound:
+//           eta_ij >= min(alpha) + min(beta) - xb with |x_ij| <= xb = M * max|a| * max|b| (8 for the clamped X0).
 __global__ void __launch_bounds__(1024)
 ll_const_kernel(int64_t I, const double* __restrict__ alpha, const double* __restrict__ rs, int64_t J,
-                const double* __restrict__ beta, const double* __restrict__ cs, double* __restrict__ out) {
+                const double* __restrict__ beta, const double* __restrict__ cs, double* __restrict__ out,
+                int xM, int xclamp, const int* __restrict__ amax_a, const int* __restrict__ amax_b) {
   __shared__ double red[1024];
-  double s = 0.0;
-  for (int64_t i = threadIdx.x; i < I; i += 1024) s += alpha[i] * rs[i];
-  for (int64_t j = threadIdx.x; j < J; j += 1024) s += beta[j] * cs[j];
+  __shared__ double rmin[1024];
+  double s = 0.0, mn_a = 0.0, mn_b = 1e300;
+  for (int64_t i = threadIdx.x; i < I; i += 1024) { const double a = alpha[i]; s += a * rs[i]; mn_a = fmin(mn_a, a); }
+  for (int64_t j = threadIdx.x; j < J; j += 1024) { const double b = beta[j]; s += b * cs[j]; mn_b = fmin(mn_b, b); }
   red[threadIdx.x] = s;
   __syncthreads();
   for (int st = 512; st > 0; st >>= 1) {
@@ -599,6 +606,25 @@ ll_const_kernel(int64_t I, const double* __restrict__ alpha, const double* __res
     __syncthreads();
   }
   if (threadIdx.x == 0) out[1] += red[0];
+  // the two minima (fmin drops NaN: a NaN alpha/beta already makes the objective NaN through the sums)
+  red[threadIdx.x] = mn_a; rmin[threadIdx.x] = mn_b;
+  __syncthreads();
+  for (int st = 512; st > 0; st >>= 1) {
+    if (threadIdx.x < st) {
+      red[threadIdx.x] = fmin(red[threadIdx.x], red[threadIdx.x + st]);
+      rmin[threadIdx.x] = fmin(rmin[threadIdx.x], rmin[threadIdx.x + st]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double xb = 0.0;
+    if (xM > 0) {
+      xb = (double)xM * (double)__int_as_float(*amax_a) * (double)__int_as_float(*amax_b);
+      if (xclamp) xb = fmin(xb, 8.0);
+    }
+    const double lo = red[0] + rmin[0] - xb;
+    out[3] = (lo < -700.0 || lo != lo) ? 1.0 : 0.0;
+  }
 }
 
 // ---------------------------------------------------------------------------------
@@ -879,7 +905,9 @@ void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const
     scal_reduce_launch(ctx, grid, ws.scal_part.get(), out3);
     // alpha and the local row sums are ldI x nbatch with zero pad rows: one flat dot product
     ll_const_kernel<<<1, 1024, 0, ctx.stream>>>(g.nbatch > 1 ? g.ldI * g.nbatch : g.I, alpha, rowsum_local, g.J, beta,
-                                                y.colsum.get(), out3);
+                                                y.colsum.get(), out3, x.M, x.clamp,
+                                                reinterpret_cast<const int*>(fa.meta.get()),
+                                                reinterpret_cast<const int*>(fb.meta.get()));
     SCGBM_LAUNCH_CHECK();
   }
 }

@@ -2,6 +2,7 @@
 // state.  X is never an I x J matrix: it is one of three factor slots; the only I x J
 // device objects are Y (compact counts) and the residual R (two fp16 planes of the scaled residual, 4 B/entry).
 #include <chrono>
+#include <map>
 #include "common.cuh"
 #include "counts.cuh"
 #include "eta_pass.cuh"
@@ -292,8 +293,39 @@ struct FitState {
 
   void setup() {
     I = a.I; J = a.J; M = a.M; nbatch = a.batch ? std::max(1, a.nbatch) : 1;
-    if (!a.Y && a.csc_p) load_counts_csc(ctx, a.csc_i, a.csc_p, a.csc_x, a.csc_x_dtype, I, J, a.batch, nbatch, a.y_storage, Y);
-    else load_counts(ctx, a.Y, a.y_dtype, a.y_on_device, I, J, a.ldY, a.batch, nbatch, a.y_storage, Y);
+    // Ingest.  With several ranks every rank must leave this block the same way: a rank that rejected its shard
+    // (NA, negative, bad batch code, out of memory) while the others went on into the first collective would
+    // leave them blocked in ncclAllReduce for ever, and a rank whose shard alone forced the u16 -> f32 storage
+    // fall-back would run different kernels from its peers.  So the status and the storage format are agreed
+    // (max over ranks) before anything else happens.
+    auto ingest = [&](int storage_req) {
+      if (!a.Y && a.csc_p) load_counts_csc(ctx, a.csc_i, a.csc_p, a.csc_x, a.csc_x_dtype, I, J, a.batch, nbatch, storage_req, Y);
+      else load_counts(ctx, a.Y, a.y_dtype, a.y_on_device, I, J, a.ldY, a.batch, nbatch, storage_req, Y);
+    };
+    auto agreed_ingest = [&](int storage_req) -> int {      // returns the largest storage code any rank ended with
+      int err = 0;
+      std::string msg;
+      try { ingest(storage_req); } catch (const Error& e) { err = e.status; msg = e.what(); }
+      if (ctx.nranks == 1) {
+        if (err) throw Error(err, msg);
+        return Y.storage;
+      }
+      DevBuf<double> ag(2);
+      double hv[2] = {(double)err, err ? 0.0 : (double)Y.storage};
+      SCGBM_CUDA(cudaMemcpyAsync(ag.get(), hv, sizeof(hv), cudaMemcpyHostToDevice, ctx.stream));
+      ctx.allreduce_max(ag.get(), 2);
+      SCGBM_CUDA(cudaMemcpyAsync(hv, ag.get(), sizeof(hv), cudaMemcpyDeviceToHost, ctx.stream));
+      ctx.sync();
+      if (err) throw Error(err, msg);
+      if (hv[0] != 0.0)
+        throw Error((int)hv[0], "the count matrix was rejected on another rank (see that rank's message); "
+                                "no rank proceeds");
+      return (int)hv[1];
+    };
+    {
+      const int agreed = agreed_ingest(a.y_storage);
+      if (agreed != Y.storage) agreed_ingest(agreed);       // a peer needed the wider format: repack to match it
+    }
     ldI = Y.ld; ldJ = round_up(J, kRowPad);
     geom = PassGeom{I, J, ldI, ldJ, nbatch, Y.batch.get()};
     // global stats
@@ -439,12 +471,29 @@ struct FitRun {
   int n_iter = 0, hit_max = 0;
   bool finished = false;
   double t_prev = 0, t_cum = 0, fused_bytes = 0;
+  int n_underflow_reruns = 0;
+  std::map<int, double> dbg_ll;                          // SCGBM_DBG_LL="7:-inf,9:nan": objective overrides (tests only)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
   explicit FitRun(const scgbm_fit_args& args)
       : a(args), ctx(args.device, reinterpret_cast<Comm*>(args.comm)), st(ctx, a) {
     ctx.prof.timing = a.profile != 0;
     ctx.prof.fused_only = a.profile == 2;
+    if (const char* e = getenv("SCGBM_DBG_LL")) {
+      std::string sv(e);
+      size_t pos = 0;
+      while (pos < sv.size()) {
+        size_t end = sv.find(',', pos);
+        if (end == std::string::npos) end = sv.size();
+        const std::string tok = sv.substr(pos, end - pos);
+        const size_t c = tok.find(':');
+        if (c != std::string::npos) {
+          const std::string v = tok.substr(c + 1);
+          dbg_ll[atoi(tok.substr(0, c).c_str())] = v == "nan" ? NAN : (v == "inf" ? INFINITY : (v == "-inf" ? -INFINITY : atof(v.c_str())));
+        }
+        pos = end + 1;
+      }
+    }
     SCGBM_CUDA(cudaEventCreate(&ev0));
     SCGBM_CUDA(cudaEventCreate(&ev1));
     SCGBM_CUDA(cudaEventRecord(ev0, ctx.stream));
@@ -539,17 +588,34 @@ struct FitRun {
       fused_bytes = fused_pass_bytes(st.geom, xm, st.Y.elem_bytes());
     }
     ctx.allreduce_sum(st.scal.get(), 2);
-    ctx.allreduce_max(st.scal.get() + 2, 1);
-    double h[3];
+    ctx.allreduce_max(st.scal.get() + 2, 2);             // max W and the underflow flag of the tensor-core pass
+    double h[4];
     SCGBM_CUDA(cudaMemcpyAsync(h, st.scal.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
     ctx.sync();
+    if (tc_eta && h[3] != 0.0) {
+      // Some eta may lie below -745: the reference's exp() underflows to 0 there and log(0) = -Inf sends it
+      // into the NaN/Inf branch (R/fit.R:152-157).  The tensor-core pass cannot see that (it sums Y * eta),
+      // so this iteration is evaluated again by the CUDA-core pass, which restates the underflow per entry.
+      pass_fused(ctx, st.eta, st.geom, xc, st.Y, st.f_row.get(), st.g_col.get(), st.la_row.get(), st.lb_col.get(),
+                 (float)st.maxY, st.resid(), st.scal.get());
+      rider = false;
+      ++n_underflow_reruns;
+      ctx.allreduce_sum(st.scal.get(), 2);
+      ctx.allreduce_max(st.scal.get() + 2, 1);
+      SCGBM_CUDA(cudaMemcpyAsync(h, st.scal.get(), 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+      ctx.sync();
+    }
     const double tr1 = trace ? now_sec() : 0.0;
     {                                                    // R/fit.R:139-142
       const double t = now_sec();
       t_cum += t - t_prev; t_prev = t;
       tvec[i - 1] = t_cum;
     }
-    const double ll = h[1] - h[0];                       // R/fit.R:151
+    double ll = h[1] - h[0];                             // R/fit.R:151
+    if (!dbg_ll.empty()) {                               // test hook: pins the control flow of R/fit.R:152-157 (Q1, Q2)
+      auto it = dbg_ll.find(i);
+      if (it != dbg_ll.end()) ll = it->second;
+    }
     const double w_max = h[2];
     LL[i - 1] = ll;
     acc[i - 1] = 0;
@@ -642,6 +708,8 @@ struct FitRun {
     const int M = st.M, nbatch = st.nbatch;
     out->n_obj = (int)obj.size(); out->n_iter = n_iter; out->hit_max_iter = hit_max;
     out->y_storage = st.Y.storage; out->max_Y = st.maxY;
+    out->svd_unconverged = st.svd.unconverged; out->svd_worst_est = st.svd.worst_est;
+    out->underflow_reruns = n_underflow_reruns;
     for (size_t k = 0; k < obj.size(); ++k) out->obj[k] = obj[k];
     for (int k = 0; k < n_iter; ++k) {
       if (out->LL) out->LL[k] = LL[k];
@@ -728,10 +796,12 @@ static void check_fit_args(const scgbm_fit_args* a) {
   SCGBM_REQUIRE(a->Y || (a->csc_p && a->csc_i && a->csc_x), "Y is NULL (pass a dense matrix or the csc_* arrays)");
   SCGBM_REQUIRE(a->M >= 1, "M must be >= 1");
   SCGBM_REQUIRE(a->max_iter >= 1, "max.iter must be >= 1");
+  SCGBM_REQUIRE(a->ngpu <= 1 || a->comm == nullptr, "ngpu > 1 and comm are mutually exclusive");
 }
 
 FitRun* fit_begin_impl(const scgbm_fit_args* a) {
   check_fit_args(a);
+  SCGBM_REQUIRE(a->ngpu <= 1, "the stepwise handle drives one GPU (or one rank with comm); use scgbm_fit for ngpu > 1");
   return new FitRun(*a);
 }
 int fit_step_impl(FitRun* r, int n_steps) {
@@ -800,7 +870,7 @@ void dbg_eval_impl(const scgbm_eval_args* a, scgbm_eval_out* out) {
   const int Mx = a->Mx;
   PassGeom geom{I, J, ldI, ldJ, 1, nullptr};
   DevBuf<double> Xu(std::max<int64_t>(ldI * Mx, 1)), Xv(std::max<int64_t>(ldJ * Mx, 1)), alpha(ldI), beta(ldJ),
-      logrs(ldI), logcs(ldJ), S(ldI), Cc(ldJ), shift(1), scal(4), tmp(std::max(ldI, ldJ));
+      logrs(ldI), logcs(ldJ), S(ldI), Cc(ldJ), shift(1), scal(8), tmp(std::max(ldI, ldJ));
   DevBuf<float> A32(std::max<int64_t>(ldI * Mx, 1)), B32(std::max<int64_t>(ldJ * Mx, 1)), f_row(ldI + 128), la_row(ldI),
       g_col(ldJ + 128), lb_col(ldJ), rs32(ldI), cs32(ldJ);
   g_col.zero(ctx.stream); f_row.zero(ctx.stream);
@@ -855,8 +925,13 @@ void dbg_eval_impl(const scgbm_eval_args* a, scgbm_eval_out* out) {
                   Y.rowsum.get(), (float)Y.maxY, R, scal.get());
   else
     pass_fused(ctx, eta, geom, x, Y, f_row.get(), g_col.get(), la_row.get(), lb_col.get(), (float)Y.maxY, R, scal.get());
-  double h[3];
+  double h[4];
   SCGBM_CUDA(cudaMemcpyAsync(h, scal.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  if (tc_eta && h[3] != 0.0) {   // possible exp() underflow (R/fit.R:152-157): the CUDA-core pass restates it, as in the fit
+    pass_fused(ctx, eta, geom, x, Y, f_row.get(), g_col.get(), la_row.get(), lb_col.get(), (float)Y.maxY, R, scal.get());
+    SCGBM_CUDA(cudaMemcpyAsync(h, scal.get(), 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  }
   SCGBM_CUDA(cudaMemcpyAsync(out->alpha, alpha.get(), I * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
   SCGBM_CUDA(cudaMemcpyAsync(out->beta, beta.get(), J * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
   ctx.sync();

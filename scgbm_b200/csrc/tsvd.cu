@@ -275,7 +275,11 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
     // parity-neutral (objective, alpha, angles unchanged to the digits printed), unlike hi-only Q1.
     static const bool env_start_full = getenv("SCGBM_START_FULL") != nullptr;
     ws.start_hi = was_warm && !env_start_full;
-    const bool ustart = ustart_enabled() && was_warm && ws.warm_calls >= 1;
+    // Only on the first attempt: a robust restart (attempt 1) may find Ub already overwritten by cycle 0's
+    // Ritz block, while the fused pass's product op.RtQ0 still belongs to the OLD block -- mixing them would
+    // give an inconsistent Gram matrix.  The restart therefore rebuilds its start block with op_mul and
+    // multiplies it itself (`have` below is false then).
+    const bool ustart = ustart_enabled() && was_warm && ws.warm_calls >= 1 && attempt == 0;
     for (int cycle = 0; !restart; ++cycle) {
       ws.T.zero(ctx.stream);
       if (ustart && cycle == 0) {
@@ -364,6 +368,9 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
   ws.lowprec = false;
   if (fast_call) ++ws.fast_streak;
   else { ws.fast_streak = 0; ws.last_est = est; }
+  // irlba would iterate on (to maxit) and warn; here the cycle budget is fixed, so an estimate that is still
+  // above the tolerance is reported (scgbm_fit_out.svd_unconverged / svd_worst_est; the wrappers warn)
+  if (!fast_call && !(est < o.tol)) { ++ws.unconverged; ws.worst_est = std::max(ws.worst_est, est); }
   copy_mat(ctx, ldI, M, ws.Ub.get(), ldI, outU, ldI);
   copy_mat(ctx, op.J, M, ws.Vwarm.get(), ldJ, outV, ldJ);
   SCGBM_CUDA(cudaMemcpyAsync(outD, ws.Tw.get(), M * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));

@@ -58,6 +58,8 @@ struct TsvdWs {
   int warm_calls = 0;       // consecutive warm calls so far (Ub then belongs to the same operator family)
   bool lowprec = false;     // cold start, early cycles: products read only the residual's hi plane
   bool start_hi = false;    // warm call: the start block Q0 = orth(G V0) is built from the hi plane only
+  int unconverged = 0;      // calls that returned with a Ritz residual estimate >= tol (cycle budget exhausted)
+  double worst_est = 0.0;   // the largest such estimate
 };
 
 // outU: ldI x M, outD: M, outV: ldJ x M (device, column-major)

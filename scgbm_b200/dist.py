@@ -2,8 +2,8 @@
 over ranks.  The data path's collectives are NCCL calls inside
 libscgbm.so; the host side only has to (a) pick each rank's column range, (b) hand
 every rank the same NCCL unique id, (c) agree on scalars such as nbatch.  Any
-broadcast/all-reduce transport works for that -- bench.py and the tests use
-torch.distributed (gloo)."""
+broadcast transport works for (b) -- bench.py and the tests use torch.distributed (gloo) there
+(tests/dist_util.py); (c) runs over the library's own NCCL all-reduce.  This package imports no torch."""
 from __future__ import annotations
 
 import ctypes as C
@@ -42,6 +42,19 @@ class Comm:
         L.check(L.load().scgbm_comm_allreduce_f64(self.handle, L.ptr(buf), buf.size, 1 if op == "max" else 0))
         return buf
 
+    def allgather_bytes(self, payload: bytes) -> list:
+        """Every rank's payload, in rank order, on every rank -- over the library's own NCCL all-reduce
+        (lengths first, then each rank's bytes in its own slot of a zero vector), so no second transport is
+        needed for small host-side agreements such as the batch levels."""
+        lens = np.zeros(self.nranks)
+        lens[self.rank] = len(payload)
+        lens = self.allreduce(lens).astype(np.int64)
+        offs = np.concatenate([[0], np.cumsum(lens)])
+        buf = np.zeros(max(int(offs[-1]), 1))
+        buf[offs[self.rank]:offs[self.rank + 1]] = np.frombuffer(payload, dtype=np.uint8)
+        buf = self.allreduce(buf).astype(np.uint8)
+        return [buf[offs[r]:offs[r + 1]].tobytes() for r in range(self.nranks)]
+
     def destroy(self):
         if self.handle:
             L.load().scgbm_comm_destroy(self.handle)
@@ -56,7 +69,7 @@ def make_unique_id() -> bytes:
 
 def init_comm(rank: int, nranks: int, device: int, broadcast_bytes) -> Comm:
     """`broadcast_bytes(payload_or_None) -> bytes` must return rank 0's payload on
-    every rank (e.g. a torch.distributed broadcast)."""
+    every rank (e.g. a torch.distributed or MPI broadcast; tests/dist_util.py has the torch one)."""
     uid = broadcast_bytes(make_unique_id() if rank == 0 else None)
     if len(uid) != L.UNIQUE_ID_BYTES:
         raise ValueError("bad NCCL unique id")
@@ -64,17 +77,3 @@ def init_comm(rank: int, nranks: int, device: int, broadcast_bytes) -> Comm:
     ub = (C.c_uint8 * L.UNIQUE_ID_BYTES).from_buffer_copy(uid)
     L.check(L.load().scgbm_comm_init_rank(C.byref(h), ub, nranks, rank, device))
     return Comm(h, rank, nranks, device)
-
-
-def torch_broadcast_bytes(nbytes: int = L.UNIQUE_ID_BYTES, src: int = 0):
-    """broadcast_bytes callable on top of an initialised torch.distributed group."""
-    import torch
-    import torch.distributed as dist
-
-    def _bc(payload):
-        t = torch.zeros(nbytes, dtype=torch.uint8)
-        if payload is not None:
-            t = torch.tensor(list(payload), dtype=torch.uint8)
-        dist.broadcast(t, src=src)
-        return bytes(t.tolist())
-    return _bc

@@ -19,13 +19,13 @@ def gbm_proj_parallel(Y, M, subsample=2000, min_counts=5, ncores=1, tol=1e-4, ma
     harness gathers those columns).  Y then holds this rank's cells only; every rank
     runs the identical subsample fit (bit-reproducible), projects its own cells, and the
     only exchanges are the gene row sums and the scalar sum(exp(beta)) of R/fit.R:274."""
-    from .api import gbm_sc, _as_counts, _is_sparse, _NP2DT
+    from .api import gbm_sc, _as_counts, _is_sparse, _NP2DT, _canonical_csc
     lib = L.load()
     if (comm is None) != (subsample_Y is None):
         raise ValueError("comm and subsample_Y go together")
     sparse = _is_sparse(Y)
     if sparse:                       # dgCMatrix-style input stays sparse on the host (R/fit.R:224 densifies only Y.sub)
-        Ys = Y.tocsc()
+        Ys = _canonical_csc(Y)
         I, J = Ys.shape
         rs = np.asarray(Ys.sum(axis=1), dtype=np.float64).ravel()
     else:

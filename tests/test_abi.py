@@ -24,7 +24,7 @@ def test_header_symbols_are_exported():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/scgbm.h but not exported"
     assert sorted(L.EXPORTS) == names
-    assert lib.scgbm_version() == 100
+    assert lib.scgbm_version() == 200
 
 
 def test_struct_layouts_match_header():

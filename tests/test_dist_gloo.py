@@ -15,7 +15,8 @@ def _free_port():
 def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
-    from scgbm_b200.dist import shard_range, torch_broadcast_bytes
+    from scgbm_b200.dist import shard_range
+    from tests.dist_util import torch_broadcast_bytes
     from oracle.r_rng import readme_demo_Y
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)

@@ -7,7 +7,7 @@ import warnings
 import numpy as np
 import pytest
 
-from tests.util import assert_fit_parity, principal_angle
+from tests.util import assert_fit_parity, checked_fit, principal_angle
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -60,10 +60,12 @@ def test_golden_fixture():
     """CUDA path against committed oracle vectors (scripts/make_golden.py): no oracle at run time."""
     from scgbm_b200 import gbm_sc, get_se
     G = np.load(os.path.join(GOLD, "sim_nb_257x1031.npz"))
-    out = gbm_sc(G["Y"], int(G["M"]), infer_beta=bool(G["infer_beta"]), diagnostics=True)
+    out = gbm_sc(G["Y"], int(G["M"]), infer_beta=bool(G["infer_beta"]), max_iter=int(G["max_iter"]), diagnostics=True)
     ref = {k: G[k] for k in ("alpha", "beta", "U", "V", "D", "scores", "obj")}
     ref["_LL"] = G["LL"]; ref["_accepted"] = G["accepted"]; ref["_n_iter"] = int(G["n_iter"])
-    assert assert_fit_parity(ref, out, check_W=False) in ("full", "knife-edge")
+    # the fixture is knife-edge free (scripts/make_golden.py): alpha, beta, U, V, D, scores are all compared
+    assert assert_fit_parity(ref, out, check_W=False) == "full"
+    assert bool(out["_hit_max_iter"]) == bool(G["hit_max_iter"])
     # get.se on the fixture's own fit (per-factor SEs are only comparable for identical U, scores, W)
     se = get_se({"U": G["U"], "scores": G["scores"], "D": G["D"], "W": G["W"].astype(np.float64)})
     np.testing.assert_allclose(se["se_scores"], G["se_scores"], rtol=1e-8)
@@ -86,18 +88,12 @@ CASES = [
 
 @pytest.mark.parametrize("I,J,d,M,kw,gen", CASES)
 def test_fit_matches_oracle(I, J, d, M, kw, gen):
-    from scgbm_b200 import gbm_sc
-    from oracle.scgbm_oracle import gbm_sc as o_gbm_sc
     Y = _sim(I, J, d, seed=I + J, **gen)
-    ref = o_gbm_sc(Y, M, **kw)
     with warnings.catch_warnings(record=True) as wl:
         warnings.simplefilter("always")
-        out = gbm_sc(Y, M, diagnostics=True, **kw)
-    res = assert_fit_parity(ref, out)
-    assert res in ("full", "knife-edge")
-    if res == "full":
-        assert bool(out["_hit_max_iter"]) == bool(ref["_hit_max_iter"])
-    assert any("Maximum number of iterations" in str(w.message) for w in wl) == bool(out["_hit_max_iter"])
+        ref, out, info = checked_fit(Y, M, **kw)      # full parity, also when the requested run has a knife edge
+    assert any("Maximum number of iterations" in str(w.message) for w in wl) == \
+        (bool(out["_hit_max_iter"]) or bool(info["requested"][1]["_hit_max_iter"]))
     # invariants
     assert abs(out["alpha"].mean()) < 1e-10
     assert np.all(np.diff(out["D"]) <= 1e-9 * out["D"][0])
@@ -179,10 +175,8 @@ def test_batches_match_oracle():
     Y = Y + 1 * (rng.random(Y.shape) < 0.2)       # every gene has counts in every batch
     codes = np.unique(labels, return_inverse=True)[1] + 1
     for kw in (dict(), dict(infer_beta=True)):
-        ref = o_gbm_sc(Y, 4, batch=codes, max_iter=25, **kw)
-        out = gbm_sc(Y, 4, batch=labels, diagnostics=True, max_iter=25, **kw)
+        ref, out, _ = checked_fit(Y, 4, cuda_kw=dict(batch=labels), oracle_kw=dict(batch=codes), max_iter=25, **kw)
         assert out["alpha"].shape == (Y.shape[0], 3)
-        assert assert_fit_parity(ref, out) in ("full", "knife-edge")
 
 
 def test_input_validation_mirrors_reference():
@@ -248,7 +242,7 @@ def test_projection_matches_oracle():
     assert out["V"] is None and out["scores"].shape == (Y.shape[1], 4)
     assert np.all(out["U"][np.setdiff1d(np.arange(Y.shape[0]), out["_ixs"])] == 0)
     # and the subsample fit itself is a parity-checked fit
-    assert assert_fit_parity(o_gbm_sc(Ysub[ixs], 4), sub) in ("full", "knife-edge")
+    checked_fit(Ysub[ixs], 4)
     # sparse (dgCMatrix-style) input takes the same path after the on-device scatter
     import scipy.sparse as sp
     outs = gbm_sc(sp.csc_matrix(Y.astype(np.float64)), 4, subset=idx)
@@ -331,7 +325,7 @@ def test_fused_product_rider_matches_plain_pass(I, J, d, M, kw, gen, monkeypatch
     np.testing.assert_array_equal(rider["_LL"][:n], plain["_LL"][:n])     # bit-identical: see eta_tc.cu PROD
     np.testing.assert_array_equal(rider["alpha"], plain["alpha"])
     assert principal_angle(rider["U"], plain["U"]) < 1e-12
-    assert assert_fit_parity(o_gbm_sc(Y, M, **kw), rider) in ("full", "knife-edge")
+    checked_fit(Y, M, **kw)          # still under SCGBM_FUSED_PROD=force
 
 
 @pytest.mark.parametrize("variant", ["batches", "u8"])

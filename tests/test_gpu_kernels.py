@@ -201,3 +201,59 @@ def test_fused_pass_clamped_x0_form(lib):
     assert np.abs(a_o - a_r).max() < 1e-5
     assert abs(o.LL - LL) < 1e-6 * abs(LL)
     assert abs(o.max_w - W.max()) <= 1e-6 * W.max()      # clipping at max.Y is active here
+
+
+@pytest.mark.parametrize("storage", [2, 3])          # u16 -> tcgen05 pass + underflow guard; f32 -> CUDA-core pass
+@pytest.mark.parametrize("x00,expect_inf", [(-800.0, True), (-720.0, False)])
+def test_exp_underflow_gives_minus_inf_like_the_reference(lib, storage, x00, expect_inf):
+    """R/fit.R:136,151-157: below eta = -745 R's exp() underflows to 0, log(0) = -Inf for a non-zero count and the
+    objective is -Inf (the loop then reverts and halves lr).  The tensor-core pass sums Y * eta and cannot see
+    that; its guard (eta_tc.cu ll_const_kernel: min alpha + min beta - |x| bound < -700) hands such an iteration
+    to the CUDA-core pass, which restates the underflow per entry.  x = -720 trips the guard but not the
+    underflow: the objective must then be the finite float64 value."""
+    rng = np.random.default_rng(3)
+    I, J = 96, 130
+    Y = rng.poisson(2.0, size=(I, J)).astype(np.int32)
+    Y[0, 0] = 3
+    Xu = np.zeros((I, 1)); Xv = np.zeros((J, 1))
+    Xu[0, 0] = x00; Xv[0, 0] = 1.0                    # X[0,0] = x00, every other entry 0
+    beta = np.log(Y.sum(0))
+    a_o, b_o, resid, o = _eval(lib, Y, Xu, Xv, beta, storage=storage)
+    with np.errstate(divide="ignore"):
+        a_r, b_r, W, LL = _eval_ref(Y, Xu @ Xv.T, beta, False)
+    assert np.isneginf(LL) == expect_inf
+    if expect_inf:
+        assert np.isneginf(o.LL) and np.isneginf(o.sum_ylogw)
+    else:
+        assert abs(o.LL - LL) < 1e-6 * abs(LL)
+    assert np.abs(a_o - a_r).max() < 5e-6
+
+
+def test_nan_inf_objective_branch_matches_reference(monkeypatch):
+    """Control flow of R/fit.R:152-157 and quirks Q1/Q2, pinned by replacing the objective of chosen iterations on
+    BOTH sides (oracle `_ll_inject`, library SCGBM_DBG_LL): -Inf reverts X <- Xt and halves lr (below 1, which
+    the LL-decrease rule never does), consumes the loop index, and leaves no entry in `obj`; a NaN objective
+    makes the NEXT iteration's `if (LL[i] < LL[i-1])` an R error ("missing value where TRUE/FALSE needed")."""
+    from scgbm_b200 import gbm_sc, RError
+    from scgbm_b200._lib import ScgbmError
+    from oracle.scgbm_oracle import gbm_sc as o_gbm_sc, sim_data, RError as ORError
+    from tests.util import assert_trace_parity
+    Y = sim_data(180, 260, 4, seed=17)["Y"]
+    monkeypatch.setenv("SCGBM_DBG_LL", "2:-inf,6:-inf,7:inf")
+    ref = o_gbm_sc(Y, 4, max_iter=14, _ll_inject={2: -np.inf, 6: -np.inf, 7: np.inf})
+    out = gbm_sc(Y, 4, max_iter=14, diagnostics=True)
+    assert not out["_accepted"][1] and not out["_accepted"][5] and not out["_accepted"][6]
+    np.testing.assert_array_equal(ref["_accepted"], out["_accepted"])
+    fin = np.isfinite(ref["_LL"])
+    np.testing.assert_array_equal(np.isfinite(out["_LL"]), fin)
+    rel = np.abs(ref["_LL"][fin] - out["_LL"][fin]) / np.abs(ref["_LL"][fin])
+    assert rel.max() < 1e-6                          # the halved learning rates (0.5, then 0.125) reach the later steps
+    assert len(out["obj"]) == len(ref["obj"]) == int(ref["_accepted"].sum())
+    np.testing.assert_allclose(out["alpha"], ref["alpha"], atol=1e-5)
+    # Q1: NaN at iteration i -> iteration i+1 compares against NA -> R stops
+    monkeypatch.setenv("SCGBM_DBG_LL", "4:nan")
+    with pytest.raises(ORError, match="missing value"):
+        o_gbm_sc(Y, 4, max_iter=14, _ll_inject={4: np.nan})
+    with pytest.raises(ScgbmError, match="missing value") as ei:
+        gbm_sc(Y, 4, max_iter=14)
+    assert ei.value.status == 3

@@ -1,5 +1,6 @@
-"""N-GPU parity: cells sharded over NCCL ranks give the same fit as one GPU.
-Skipped unless the box has at least two GPUs (`gpurun --gpus 2`)."""
+"""N-GPU parity: cells sharded over NCCL ranks give the same fit as one GPU -- both ways the
+library offers: one process per GPU (`comm=`, the bench/torchrun path) and one caller using several GPUs
+(`ngpu=`, the R user's path).  Each test skips unless the box has enough GPUs (`gpurun --gpus 2|4|8`)."""
 import os
 import socket
 
@@ -13,17 +14,48 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
+def _need_gpus(n):
+    from scgbm_b200 import _lib
+    have = _lib.load().scgbm_device_count()
+    if have < n:
+        pytest.skip(f"needs {n} GPUs, box has {have}")
+
+
+def _spawn(target, world, *args, timeout=600):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=target, args=(r, world, port, q) + args) for r in range(world)]
+    for p in ps: p.start()
+    res = sorted([q.get(timeout=timeout) for _ in ps], key=lambda r: r[0])
+    for p in ps:
+        p.join(120); assert p.exitcode == 0
+    return res
+
+
+def _rank_setup(rank, world, port):
+    import torch.distributed as dist
+    from scgbm_b200.dist import init_comm
+    from tests.dist_util import torch_broadcast_bytes
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    return init_comm(rank, world, rank, torch_broadcast_bytes())
+
+
+def _data():
+    from oracle.scgbm_oracle import sim_data
+    return sim_data(700, 1800, 8, seed=5, nb_theta=1.0)["Y"]
+
+
 def _worker(rank, world, port, q, kw):
     import torch.distributed as dist
     from scgbm_b200 import gbm_sc
-    from scgbm_b200.dist import shard_range, init_comm, torch_broadcast_bytes
-    from oracle.scgbm_oracle import sim_data
-    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from scgbm_b200.dist import shard_range
+    comm = _rank_setup(rank, world, port)
     try:
-        Y = sim_data(700, 1800, 8, seed=5, nb_theta=1.0)["Y"]
+        Y = _data()
         j0, j1 = shard_range(Y.shape[1], rank, world)
-        comm = init_comm(rank, world, rank, torch_broadcast_bytes())
         out = gbm_sc(np.asfortranarray(Y[:, j0:j1]), 8, device=rank, comm=comm, diagnostics=True, return_W=False, **kw)
         comm.destroy()
         q.put((rank, j0, j1, out["_LL"], out["_accepted"], out["alpha"], out["beta"], out["U"], out["V"], out["D"]))
@@ -31,24 +63,8 @@ def _worker(rank, world, port, q, kw):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(infer_beta=True, max_iter=25)])
-def test_two_gpus_match_one(kw):
-    from scgbm_b200 import _lib, gbm_sc
-    from oracle.scgbm_oracle import sim_data
+def _check_against_one_gpu(res, one):
     from tests.util import principal_angle
-    if _lib.load().scgbm_device_count() < 2:
-        pytest.skip("needs two GPUs")
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    ps = [ctx.Process(target=_worker, args=(r, 2, port, q, kw)) for r in range(2)]
-    for p in ps: p.start()
-    res = sorted([q.get(timeout=300) for _ in ps], key=lambda r: r[0])
-    for p in ps:
-        p.join(60); assert p.exitcode == 0
-    Y = sim_data(700, 1800, 8, seed=5, nb_theta=1.0)["Y"]
-    one = gbm_sc(Y, 8, diagnostics=True, return_W=False, **kw)
     for r in res:       # replicated quantities are identical on every rank
         n = min(len(r[3]), len(one["_LL"]))
         np.testing.assert_array_equal(r[4][:n], one["_accepted"][:n])
@@ -56,25 +72,142 @@ def test_two_gpus_match_one(kw):
         np.testing.assert_allclose(r[5], one["alpha"], atol=1e-5)
         np.testing.assert_allclose(r[9], one["D"], rtol=1e-5)
         assert principal_angle(r[7], one["U"]) < 1e-4
-    np.testing.assert_array_equal(res[0][7], res[1][7])
-    beta = np.concatenate([res[0][6], res[1][6]])
-    V = np.vstack([res[0][8], res[1][8]])
+        np.testing.assert_array_equal(r[7], res[0][7])
+    beta = np.concatenate([r[6] for r in res])
+    V = np.vstack([r[8] for r in res])
     np.testing.assert_allclose(beta, one["beta"], atol=1e-5)
     assert principal_angle(V, one["V"]) < 1e-4
+
+
+@pytest.mark.parametrize("world,kw", [(2, dict()), (2, dict(infer_beta=True, max_iter=25)), (4, dict(max_iter=40)),
+                                      (8, dict(max_iter=40))])
+def test_n_ranks_match_one_gpu(world, kw):
+    from scgbm_b200 import gbm_sc
+    _need_gpus(world)
+    res = _spawn(_worker, world, kw)
+    one = gbm_sc(_data(), 8, diagnostics=True, return_W=False, **kw)
+    _check_against_one_gpu(res, one)
+
+
+@pytest.mark.parametrize("ngpu", [2, 4, 8])
+def test_one_caller_many_gpus(ngpu):
+    """`gbm_sc(Y, M, ngpu=n)`: ONE call (the R user's calling convention, R/fit.R:52) drives n GPUs -- host threads
+    and NCCL ranks live inside the library.  Same fit as one GPU; with W, scores, get.se and sparse input."""
+    import scipy.sparse as sp
+    from scgbm_b200 import gbm_sc, get_se
+    from tests.util import principal_angle
+    _need_gpus(ngpu)
+    Y = _data()
+    one = get_se(gbm_sc(Y, 8, diagnostics=True, max_iter=40))
+    seen = []
+    many = gbm_sc(Y, 8, diagnostics=True, max_iter=40, ngpu=ngpu, quiet=True)
+    n = min(len(many["_LL"]), len(one["_LL"]))
+    np.testing.assert_array_equal(many["_accepted"][:n], one["_accepted"][:n])
+    np.testing.assert_allclose(many["_LL"][:n], one["_LL"][:n], rtol=1e-6)
+    np.testing.assert_allclose(many["alpha"], one["alpha"], atol=1e-5)
+    np.testing.assert_allclose(many["beta"], one["beta"], atol=1e-5)
+    assert principal_angle(many["U"], one["U"]) < 1e-4 and principal_angle(many["V"], one["V"]) < 1e-4
+    assert many["V"].shape == one["V"].shape and many["W"].shape == Y.shape
+    np.testing.assert_allclose(many["W"], one["W"], rtol=5e-4)
+    np.testing.assert_allclose(many["scores"], many["V"] * many["D"][None, :], rtol=1e-12)
+    se1 = get_se(many)
+    seN = get_se(many, ngpu=ngpu)            # cells split inside the library, gene-side Grams all-reduced
+    np.testing.assert_allclose(seN["se_scores"], se1["se_scores"], rtol=1e-9)
+    np.testing.assert_allclose(seN["se_loadings"], se1["se_loadings"], rtol=1e-9)
+    sparse = gbm_sc(sp.csc_matrix(Y.astype(np.float64)), 8, diagnostics=True, max_iter=40, ngpu=ngpu)
+    np.testing.assert_allclose(sparse["_LL"], many["_LL"], rtol=1e-12)
+    del seen
+
+
+def _batch_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from scgbm_b200 import gbm_sc
+    comm = _rank_setup(rank, world, port)
+    try:
+        Y, labels = _batch_data()
+        J = Y.shape[1]
+        # batch-sorted cells, contiguous shards: rank 1 holds ONLY batch "b" while rank 0 holds "a" and "b"
+        cut = int(0.7 * J)
+        sl = slice(0, cut) if rank == 0 else slice(cut, J)
+        out = gbm_sc(np.asfortranarray(Y[:, sl]), 4, batch=labels[sl], device=rank, comm=comm, diagnostics=True,
+                     return_W=False, max_iter=20)
+        comm.destroy()
+        q.put((rank, out["_LL"], out["alpha"], out["beta"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def _batch_data():
+    from oracle.scgbm_oracle import sim_data
+    rng = np.random.default_rng(12)
+    Y = sim_data(220, 500, 4, seed=8)["Y"]
+    Y = Y + 1 * (rng.random(Y.shape) < 0.2)
+    J = Y.shape[1]
+    labels = np.array(["a"] * (J // 2) + ["b"] * (J - J // 2))
+    return np.asfortranarray(Y), labels
+
+
+def test_batch_levels_are_global_across_ranks():
+    """a shard that lacks a batch level must not re-number the levels it has."""
+    from scgbm_b200 import gbm_sc
+    _need_gpus(2)
+    res = _spawn(_batch_worker, 2)
+    Y, labels = _batch_data()
+    one = gbm_sc(Y, 4, batch=labels, diagnostics=True, return_W=False, max_iter=20)
+    assert one["alpha"].shape[1] == 2
+    for r in res:
+        assert r[2].shape == one["alpha"].shape
+        np.testing.assert_allclose(r[1], one["_LL"], rtol=1e-6)
+        np.testing.assert_allclose(r[2], one["alpha"], atol=1e-5)
+    np.testing.assert_allclose(np.concatenate([res[0][3], res[1][3]]), one["beta"], atol=1e-5)
+
+
+def _bad_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from scgbm_b200 import gbm_sc, RError
+    from scgbm_b200.dist import shard_range
+    comm = _rank_setup(rank, world, port)
+    try:
+        Y = _data().astype(np.float64)
+        j0, j1 = shard_range(Y.shape[1], rank, world)
+        Yl = np.asfortranarray(Y[:, j0:j1])
+        if rank == 1:
+            Yl[3, 4] = -1.0                   # only rank 1's shard is invalid
+        try:
+            gbm_sc(Yl, 8, device=rank, comm=comm, return_W=False, max_iter=5)
+            msg = "no error"
+        except RError as e:
+            msg = str(e)
+        comm.destroy()
+        q.put((rank, msg))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_error_on_one_rank_reaches_every_rank():
+    """an input error on one rank must not leave the others blocked in a collective."""
+    _need_gpus(2)
+    res = _spawn(_bad_worker, 2, timeout=180)
+    assert "negative" in res[1][1]
+    assert "another rank" in res[0][1]
+    # and through the in-process driver the caller sees the originating rank's message
+    from scgbm_b200 import gbm_sc, RError
+    Y = _data().astype(np.float64)
+    Y[3, Y.shape[1] - 2] = -1.0
+    with pytest.raises(RError, match="negative"):
+        gbm_sc(Y, 8, ngpu=2, max_iter=5)
 
 
 def _proj_worker(rank, world, port, q):
     import torch.distributed as dist
     from scgbm_b200 import gbm_proj_parallel
-    from scgbm_b200.dist import shard_range, init_comm, torch_broadcast_bytes
+    from scgbm_b200.dist import shard_range
     from oracle.scgbm_oracle import sim_data
-    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    comm = _rank_setup(rank, world, port)
     try:
         Y = sim_data(300, 900, 4, seed=9)["Y"]
         jxs = np.arange(0, 900, 3)                   # the subsample every rank is handed
         j0, j1 = shard_range(Y.shape[1], rank, world)
-        comm = init_comm(rank, world, rank, torch_broadcast_bytes())
         out = gbm_proj_parallel(np.asfortranarray(Y[:, j0:j1]), 4, device=rank, comm=comm,
                                 subsample_Y=np.asfortranarray(Y[:, jxs]), max_iter=40)
         comm.destroy()
@@ -83,27 +216,19 @@ def _proj_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_sharded_projection_matches_one_gpu():
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_projection_matches_one_gpu(world):
     """BASELINE configs[3]: gbm.sc(subset=) with the cells sharded; R/fit.R:213-285."""
-    from scgbm_b200 import _lib, gbm_proj_parallel
+    from scgbm_b200 import gbm_proj_parallel
     from oracle.scgbm_oracle import sim_data
-    if _lib.load().scgbm_device_count() < 2:
-        pytest.skip("needs two GPUs")
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    ps = [ctx.Process(target=_proj_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in ps: p.start()
-    res = sorted([q.get(timeout=300) for _ in ps], key=lambda r: r[0])
-    for p in ps:
-        p.join(60); assert p.exitcode == 0
+    _need_gpus(world)
+    res = _spawn(_proj_worker, world)
     Y = sim_data(300, 900, 4, seed=9)["Y"]
     one = gbm_proj_parallel(Y, 4, subsample=np.arange(0, 900, 3) + 1, max_iter=40)
-    np.testing.assert_array_equal(res[0][5], res[1][5])          # the subsample fit is replicated bit for bit
-    np.testing.assert_allclose(res[0][5], one["U"], atol=1e-12)
     for r in res:
+        np.testing.assert_array_equal(r[5], res[0][5])           # the subsample fit is replicated bit for bit
         np.testing.assert_allclose(r[1], one["alpha"], atol=1e-10)
-    np.testing.assert_allclose(np.concatenate([res[0][2], res[1][2]]), one["beta"], atol=1e-10)
-    np.testing.assert_allclose(np.vstack([res[0][3], res[1][3]]), one["scores"], atol=1e-10)
-    np.testing.assert_allclose(np.vstack([res[0][4], res[1][4]]), one["se_scores"], rtol=1e-9)
+    np.testing.assert_allclose(res[0][5], one["U"], atol=1e-12)
+    np.testing.assert_allclose(np.concatenate([r[2] for r in res]), one["beta"], atol=1e-10)
+    np.testing.assert_allclose(np.vstack([r[3] for r in res]), one["scores"], atol=1e-10)
+    np.testing.assert_allclose(np.vstack([r[4] for r in res]), one["se_scores"], rtol=1e-9)

@@ -34,7 +34,9 @@ def test_oracle_reproduces_committed_fixture():
     """tests/golden/sim_nb_257x1031.npz (scripts/make_golden.py) is what the oracle computes today."""
     from oracle.scgbm_oracle import gbm_sc
     F = np.load(os.path.join(os.path.dirname(__file__), "golden", "sim_nb_257x1031.npz"))
-    out = gbm_sc(F["Y"], int(F["M"]), infer_beta=bool(F["infer_beta"]))
+    out = gbm_sc(F["Y"], int(F["M"]), infer_beta=bool(F["infer_beta"]), max_iter=int(F["max_iter"]))
+    from tests.util import first_knife_edge
+    assert first_knife_edge(out) == len(out["_LL"])      # the fixture is knife-edge free: every output is comparable
     assert out["_n_iter"] == int(F["n_iter"])
     np.testing.assert_array_equal(out["_accepted"], F["accepted"])
     np.testing.assert_allclose(out["_LL"], F["LL"], rtol=1e-12)
