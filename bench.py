@@ -140,6 +140,20 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def torch_broadcast_bytes(nbytes=128, src=0):
+    """rendezvous only: hands every rank the NCCL unique id of libscgbm over torch.distributed (gloo)."""
+    import torch
+    import torch.distributed as dist
+
+    def _bc(payload):
+        t = torch.zeros(nbytes, dtype=torch.uint8)
+        if payload is not None:
+            t = torch.tensor(list(payload), dtype=torch.uint8)
+        dist.broadcast(t, src=src)
+        return bytes(t.tolist())
+    return _bc
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -216,7 +230,7 @@ def main():
         return
 
     from scgbm_b200 import _lib as L, gbm_sc
-    from scgbm_b200.dist import shard_range, init_comm, torch_broadcast_bytes
+    from scgbm_b200.dist import shard_range, init_comm
     lib = L.load()
     device = local_rank
     comm = None

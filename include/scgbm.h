@@ -162,6 +162,8 @@ typedef struct scgbm_fit_out {
   int32_t underflow_reruns; /* iterations re-evaluated on the CUDA-core pass because exp(eta) could underflow
                              * in the reference's doubles (log(0) = -Inf branch, R/fit.R:152-157)            */
   double  svd_worst_est;
+  int64_t exact_rows;       /* gene row sums re-summed in fp64 over all iterations because |x| in the row grew
+                             * beyond what the 22-bit tensor-core eta resolves to the alpha tolerance (12)   */
 } scgbm_fit_out;
 
 int scgbm_fit(const scgbm_fit_args* args, scgbm_fit_out* out);
@@ -262,6 +264,70 @@ typedef struct scgbm_sim_args {
 /* writes counts into the DEVICE buffer `Y_dev` (I x J, leading dim ld); returns the
  * number of entries that saturated the output type in *n_saturated. */
 int scgbm_sim_counts(const scgbm_sim_args* args, void* Y_dev, int64_t* n_saturated);
+
+/* ---- simData / simNull / simNullNB entirely on the device (R/simulate.R:24-48, :51-57, :60-65) ----
+ * The reference's only other exported compute function (NAMESPACE:10) and the generator of every benchmark
+ * input.  Everything is drawn on the GPU from one counter-based stream (Philox4x32-10 keyed by `seed`, one
+ * counter per drawn element, so shards and launch geometry do not matter):
+ *   SCGBM_SIM_DATA     U (I x d), V (J_total x d): Haar on the Stiefel manifold = QR of a Gaussian with
+ *                      positive diag(R) (Cholesky-QR on device; rstiefel::rustiefel [ext] draws from the same
+ *                      distribution), signs fixed so that U[1, m] >= 0 (:28-33);
+ *                      D = seq(K (sqrt I + sqrt J), sqrt I + sqrt J, length.out = d) (:27);
+ *                      alpha_i ~ N(alpha_mean, 1), beta_j ~ N(beta_mean, 1) (:35-36);
+ *                      Y_ij ~ Poisson(exp(alpha_i + beta_j + (U D V^T)_ij)) (:37-38); theta > 0 draws
+ *                      negative-binomial counts of that mean instead (MASS::rnegbin parametrisation, :63).
+ *   SCGBM_SIM_NULL     mu_i ~ U(1, 10), Y_ij ~ Poisson(mu_i)                      (:51-57)
+ *   SCGBM_SIM_NULL_NB  mu_i ~ U(1, 10), Y_ij ~ NB(mu_i, theta)                    (:60-65)
+ * A call generates the cells [j_offset, j_offset + J) of a J_total-cell matrix; the gene-side draws and D
+ * depend on (seed, I, J_total, d) only, so the shards of several ranks fit together. */
+enum scgbm_sim_model { SCGBM_SIM_DATA = 0, SCGBM_SIM_NULL = 1, SCGBM_SIM_NULL_NB = 2 };
+
+typedef struct scgbm_simdata_args {
+  int32_t  model;        /* scgbm_sim_model                                                 */
+  int32_t  d;            /* latent factors (SCGBM_SIM_DATA)                                 */
+  int64_t  I, J;         /* genes; cells generated by THIS call                             */
+  int64_t  J_total;      /* cells of the whole matrix (0: = J)                              */
+  int64_t  j_offset;     /* global index of this call's first cell                          */
+  double   alpha_mean, beta_mean, K;   /* R defaults 0, 0, 2                                */
+  double   theta;        /* simNullNB: R default 1;  SCGBM_SIM_DATA: > 0 -> NB counts       */
+  uint64_t seed;
+  int32_t  out_dtype;    /* element type of Y: SCGBM_U8 / U16 / F32 / I32                   */
+  int32_t  y_on_device;  /* out->Y is a device pointer                                      */
+  int64_t  ldY;          /* leading dimension of out->Y (>= I; pad rows are written as 0)   */
+  int32_t  device;
+} scgbm_simdata_args;
+
+typedef struct scgbm_simdata_out {
+  void*   Y;             /* I x J counts, column-major, leading dim ldY                     */
+  /* host, caller-allocated, each may be NULL: */
+  double* U;             /* I x d      val$U                                                */
+  double* V;             /* J x d      val$V = V diag(D) (ground-truth scores), this call's cells */
+  double* D;             /* d          val$D                                                */
+  double* alpha;         /* I          val$alpha  (null models: log(mu_i))                  */
+  double* beta;          /* J          val$beta   (null models: 0)                          */
+  int64_t n_saturated;   /* entries clipped to the maximum of out_dtype                     */
+} scgbm_simdata_out;
+
+int scgbm_sim_data(const scgbm_simdata_args* args, scgbm_simdata_out* out);
+
+/* ---- CCI perturbation sampling (R/cci.R:69-71; the null draw of :57,:104) ---------------------------
+ *   out[, , r] = scores + e_r,   e_r[j, m] ~ N(0, se_scores[j, m]^2),   r = 0 .. reps-1
+ * -- the `V.new <- V + matrix(rnorm(J*M, sd = se_V), J, M)` that CCI() feeds to the user's clustering
+ * function `reps` times -- as ONE batched device op.  scores == NULL gives e_r alone (V.null, R/cci.R:57).
+ * Draw r of the stream is (seed, rep_offset + r), so R can fetch the replicates in batches. */
+typedef struct scgbm_cci_args {
+  int64_t  J;
+  int32_t  M;
+  const double* scores;     /* J x M (gbm$scores) or NULL                                   */
+  const double* se_scores;  /* J x M (gbm$se_scores)                                        */
+  int32_t  reps;
+  int32_t  rep_offset;
+  uint64_t seed;
+  int32_t  out_on_device;   /* `out` is a device pointer                                    */
+  int32_t  device;
+} scgbm_cci_args;
+
+int scgbm_cci_perturb(const scgbm_cci_args* args, double* out /* J x M x reps, column-major */);
 
 /* ---- device memory helpers for callers that keep Y resident ------------------- */
 int scgbm_dev_alloc(void** p, int64_t bytes, int device);

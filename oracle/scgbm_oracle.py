@@ -150,8 +150,10 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
     LRA = None
     n_iter = 0
     hit_max = False
+    alpha_xmax = None
     for i in range(1, max_iter + 1):                                   # :125
         n_iter = i
+        alpha_xmax = np.abs(X).max(axis=1)   # diagnostic: max_j |X_ij| of the X this trip's alpha is solved from
         with np.errstate(divide="ignore", over="ignore", invalid="ignore"):
             for k in range(nbatch):                                    # :127-130
                 sel = bidx == k
@@ -223,6 +225,7 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
     out["_lr"] = np.array(lr_trace)
     out["_n_iter"] = n_iter
     out["_hit_max_iter"] = hit_max
+    out["_alpha_xmax"] = alpha_xmax
     return out
 
 

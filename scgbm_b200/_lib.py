@@ -64,7 +64,8 @@ class FitOut(C.Structure):
                 ("n_obj", C.c_int32), ("n_iter", C.c_int32), ("hit_max_iter", C.c_int32),
                 ("y_storage", C.c_int32), ("max_Y", C.c_double), ("prof", Profile),
                 ("Xu", C.c_void_p), ("Xv", C.c_void_p), ("x_rank", C.c_int32),
-                ("svd_unconverged", C.c_int32), ("underflow_reruns", C.c_int32), ("svd_worst_est", C.c_double)]
+                ("svd_unconverged", C.c_int32), ("underflow_reruns", C.c_int32), ("svd_worst_est", C.c_double),
+                ("exact_rows", C.c_int64)]
 
 
 class SeArgs(C.Structure):
@@ -100,6 +101,24 @@ class SimArgs(C.Structure):
                 ("d", C.c_int32), ("U", C.c_void_p), ("V", C.c_void_p), ("D", C.c_void_p),
                 ("alpha", C.c_void_p), ("beta", C.c_void_p), ("nb_theta", C.c_double),
                 ("seed", C.c_uint64), ("out_dtype", C.c_int32), ("device", C.c_int32)]
+
+
+class SimDataArgs(C.Structure):
+    _fields_ = [("model", C.c_int32), ("d", C.c_int32), ("I", C.c_int64), ("J", C.c_int64), ("J_total", C.c_int64),
+                ("j_offset", C.c_int64), ("alpha_mean", C.c_double), ("beta_mean", C.c_double), ("K", C.c_double),
+                ("theta", C.c_double), ("seed", C.c_uint64), ("out_dtype", C.c_int32), ("y_on_device", C.c_int32),
+                ("ldY", C.c_int64), ("device", C.c_int32)]
+
+
+class SimDataOut(C.Structure):
+    _fields_ = [("Y", C.c_void_p), ("U", C.c_void_p), ("V", C.c_void_p), ("D", C.c_void_p), ("alpha", C.c_void_p),
+                ("beta", C.c_void_p), ("n_saturated", C.c_int64)]
+
+
+class CciArgs(C.Structure):
+    _fields_ = [("J", C.c_int64), ("M", C.c_int32), ("scores", C.c_void_p), ("se_scores", C.c_void_p),
+                ("reps", C.c_int32), ("rep_offset", C.c_int32), ("seed", C.c_uint64), ("out_on_device", C.c_int32),
+                ("device", C.c_int32)]
 
 
 class TsvdArgs(C.Structure):
@@ -144,6 +163,7 @@ class EvalOut(C.Structure):
 # every symbol include/scgbm.h declares
 EXPORTS = [
     "scgbm_fit", "scgbm_fit_begin", "scgbm_fit_step", "scgbm_fit_profile", "scgbm_fit_set_profile", "scgbm_fit_end", "scgbm_get_se", "scgbm_project", "scgbm_sim_counts",
+    "scgbm_sim_data", "scgbm_cci_perturb",
     "scgbm_dev_alloc", "scgbm_dev_free", "scgbm_memcpy_d2h", "scgbm_memcpy_h2d",
     "scgbm_host_alloc_pinned", "scgbm_host_free_pinned", "scgbm_flush_l2",
     "scgbm_comm_unique_id", "scgbm_comm_init_rank", "scgbm_comm_destroy", "scgbm_comm_allreduce_f64",
@@ -175,6 +195,8 @@ def load():
     lib.scgbm_get_se.argtypes = [C.POINTER(SeArgs), C.POINTER(SeOut)]
     lib.scgbm_project.argtypes = [C.POINTER(ProjArgs), C.POINTER(ProjOut)]
     lib.scgbm_sim_counts.argtypes = [C.POINTER(SimArgs), C.c_void_p, C.POINTER(C.c_int64)]
+    lib.scgbm_sim_data.argtypes = [C.POINTER(SimDataArgs), C.POINTER(SimDataOut)]
+    lib.scgbm_cci_perturb.argtypes = [C.POINTER(CciArgs), C.c_void_p]
     lib.scgbm_dev_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64, C.c_int]
     lib.scgbm_dev_free.argtypes = [C.c_void_p, C.c_int]
     lib.scgbm_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]

@@ -225,6 +225,7 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
         out["_svd_unconverged"] = int(o.svd_unconverged)
         out["_svd_worst_est"] = float(o.svd_worst_est)
         out["_underflow_reruns"] = int(o.underflow_reruns)
+        out["_exact_rows"] = int(o.exact_rows)
     return out
 
 

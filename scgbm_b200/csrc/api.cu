@@ -22,6 +22,8 @@ void fit_end_impl(FitRun* r, scgbm_fit_out* out);
 void get_se_impl(const scgbm_se_args* a, scgbm_se_out* out);
 void project_impl(const scgbm_proj_args* a, scgbm_proj_out* out);
 void sim_counts(const scgbm_sim_args* a, void* Y_dev, int64_t* n_saturated);
+void sim_data_impl(const scgbm_simdata_args* a, scgbm_simdata_out* out);
+void cci_perturb_impl(const scgbm_cci_args* a, double* out);
 void dbg_tsvd_impl(const scgbm_tsvd_args* a, scgbm_tsvd_out* out);
 void dbg_eval_impl(const scgbm_eval_args* a, scgbm_eval_out* out);
 void dbg_prod_impl(const scgbm_prod_args* a, scgbm_prod_out* out);
@@ -83,6 +85,8 @@ int scgbm_project(const scgbm_proj_args* args, scgbm_proj_out* out) { return gua
 int scgbm_sim_counts(const scgbm_sim_args* args, void* Y_dev, int64_t* n_saturated) {
   return guarded([&] { SCGBM_REQUIRE(args && Y_dev, "NULL args"); sim_counts(args, Y_dev, n_saturated); });
 }
+int scgbm_sim_data(const scgbm_simdata_args* args, scgbm_simdata_out* out) { return guarded([&] { sim_data_impl(args, out); }); }
+int scgbm_cci_perturb(const scgbm_cci_args* args, double* out) { return guarded([&] { cci_perturb_impl(args, out); }); }
 
 int scgbm_dev_alloc(void** p, int64_t bytes, int device) {
   return guarded([&] {

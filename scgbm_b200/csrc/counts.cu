@@ -367,180 +367,4 @@ void load_counts_rows(Ctx& ctx, const void* Y, int y_dtype, int y_on_device, int
   load_impl(ctx, Y, y_dtype, y_on_device, I_full, J, ldY, ixs_host, Ik, nullptr, 1, SCGBM_STORE_AUTO, c);
 }
 
-// ---------------------------------------------------------------------------------
-// on-device generator: Y ~ Poisson / NB(exp(alpha_i + beta_j + (U D V^T)_ij))
-// counter-based Philox4x32-10 keyed by (seed, element index) so shards are
-// reproducible independently of the launch geometry.
-// ---------------------------------------------------------------------------------
-struct Philox {
-  uint32_t c[4], k[2], out[4];
-  int have;
-  __device__ Philox(uint64_t seed, uint64_t idx) {
-    c[0] = (uint32_t)idx; c[1] = (uint32_t)(idx >> 32); c[2] = 0; c[3] = 0x5C6B0000u;
-    k[0] = (uint32_t)seed; k[1] = (uint32_t)(seed >> 32);
-    have = 0;
-  }
-  __device__ void round_fn(uint32_t* ctr, const uint32_t* key) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr[0]), lo0 = 0xD2511F53u * ctr[0];
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr[2]), lo1 = 0xCD9E8D57u * ctr[2];
-    const uint32_t n0 = hi1 ^ ctr[1] ^ key[0], n1 = lo1, n2 = hi0 ^ ctr[3] ^ key[1], n3 = lo0;
-    ctr[0] = n0; ctr[1] = n1; ctr[2] = n2; ctr[3] = n3;
-  }
-  __device__ void refill() {
-    uint32_t ctr[4] = {c[0], c[1], c[2], c[3]};
-    uint32_t key[2] = {k[0], k[1]};
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      round_fn(ctr, key);
-      key[0] += 0x9E3779B9u; key[1] += 0xBB67AE85u;
-    }
-    out[0] = ctr[0]; out[1] = ctr[1]; out[2] = ctr[2]; out[3] = ctr[3];
-    c[2] += 1;
-    have = 4;
-  }
-  __device__ uint32_t next() {
-    if (have == 0) refill();
-    return out[--have];
-  }
-  __device__ double uniform() {  // (0,1), 53-bit
-    const uint64_t a = next() >> 5, b = next() >> 6;
-    return ((double)a * 67108864.0 + (double)b + 0.5) * (1.0 / 9007199254740992.0);
-  }
-  __device__ double normal() {
-    const double u1 = uniform(), u2 = uniform();
-    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
-  }
-  __device__ double gamma(double shape) {  // Marsaglia-Tsang
-    double boost = 1.0;
-    if (shape < 1.0) { boost = pow(uniform(), 1.0 / shape); shape += 1.0; }
-    const double d = shape - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * d);
-    for (int it = 0; it < 1000; ++it) {
-      double x = normal(), v = 1.0 + cc * x;
-      if (v <= 0.0) continue;
-      v = v * v * v;
-      const double u = uniform();
-      if (u < 1.0 - 0.0331 * x * x * x * x) return boost * d * v;
-      if (log(u) < 0.5 * x * x + d * (1.0 - v + log(v))) return boost * d * v;
-    }
-    return boost * d;
-  }
-  __device__ double poisson(double lam) {
-    if (!(lam > 0.0)) return 0.0;
-    if (lam < 12.0) {   // inversion by sequential search
-      const double u = uniform();
-      double p = exp(-lam), q = p;
-      int k = 0;
-      while (u > q && k < 200) { ++k; p *= lam / k; q += p; }
-      return (double)k;
-    }
-    // PTRS (Hoermann 1993)
-    const double slam = sqrt(lam), loglam = log(lam);
-    const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
-    const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
-    for (int it = 0; it < 1000; ++it) {
-      const double U = uniform() - 0.5, V = uniform();
-      const double us = 0.5 - fabs(U);
-      const double k = floor((2.0 * a / us + b) * U + lam + 0.43);
-      if (us >= 0.07 && V <= vr) return k;
-      if (k < 0.0 || (us < 0.013 && V > us)) continue;
-      if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -lam + k * loglam - lgamma(k + 1.0)) return k;
-    }
-    return floor(lam);
-  }
-};
-
-template <typename Tout> struct SimLimit;
-template <> struct SimLimit<uint8_t> { static constexpr double max = 255.0; };
-template <> struct SimLimit<uint16_t> { static constexpr double max = 65535.0; };
-template <> struct SimLimit<float> { static constexpr double max = 16777216.0; };
-template <> struct SimLimit<int32_t> { static constexpr double max = 2147483647.0; };
-
-template <typename Tout>
-__global__ void __launch_bounds__(256)
-sim_counts_kernel(int64_t I, int64_t J, int64_t ld, int64_t j_offset, int d, const float* __restrict__ Ud,
-                  const float* __restrict__ V, const float* __restrict__ alpha, const float* __restrict__ beta,
-                  double nb_theta, uint64_t seed, Tout* __restrict__ Y, unsigned long long* __restrict__ n_sat) {
-  extern __shared__ float s_v[];   // d floats: V row of this column
-  const int64_t j = blockIdx.y;
-  for (int m = threadIdx.x; m < d; m += blockDim.x) s_v[m] = V[(int64_t)m * J + j];
-  __syncthreads();
-  const float bj = beta[j];
-  unsigned long long sat = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ld; i += (int64_t)gridDim.x * blockDim.x) {
-    Tout outv = (Tout)0;
-    if (i < I) {
-      float x = alpha[i] + bj;
-      for (int m = 0; m < d; ++m) x = fmaf(Ud[(int64_t)m * I + i], s_v[m], x);
-      double lam = exp((double)x);
-      Philox rng(seed, (uint64_t)(j_offset + j) * (uint64_t)I + (uint64_t)i);
-      if (nb_theta > 0.0) lam = rng.gamma(nb_theta) * (lam / nb_theta);
-      double y = rng.poisson(lam);
-      if (y > SimLimit<Tout>::max) { y = SimLimit<Tout>::max; ++sat; }
-      outv = (Tout)y;
-    }
-    Y[j * ld + i] = outv;
-  }
-  if (sat) atomicAdd(n_sat, sat);
-}
-
-__global__ void f64_to_f32_scaled(int64_t n, int q, const double* __restrict__ src, int64_t lds,
-                                  const double* __restrict__ colscale, float* __restrict__ dst, int64_t ldd) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * q) return;
-  const int64_t r = idx % n;
-  const int c = (int)(idx / n);
-  dst[(int64_t)c * ldd + r] = (float)(src[(int64_t)c * lds + r] * (colscale ? colscale[c] : 1.0));
-}
-
-void sim_counts(const scgbm_sim_args* a, void* Y_dev, int64_t* n_saturated) {
-  SCGBM_REQUIRE(a->I >= 1 && a->J >= 1 && a->ld >= a->I, "sim: bad shape");
-  SCGBM_REQUIRE(a->d >= 0 && a->d <= 1024, "sim: bad d");
-  SCGBM_REQUIRE(a->alpha && a->beta, "sim: alpha/beta required");
-  Ctx ctx(a->device, nullptr);
-  const int64_t I = a->I, J = a->J;
-  const int d = a->d;
-  DevBuf<double> tmp(std::max<int64_t>(std::max(I, J) * std::max(d, 1), 1)), Dd(std::max(d, 1));
-  DevBuf<float> Ud(std::max<int64_t>(I * d, 1)), Vf(std::max<int64_t>(J * d, 1)), al(I), be(J);
-  auto conv = [&](const double* host, int64_t n, int q, const double* colscale_dev, float* dst) {
-    SCGBM_CUDA(cudaMemcpyAsync(tmp.get(), host, n * q * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
-    f64_to_f32_scaled<<<(unsigned)ceil_div(n * q, 256), 256, 0, ctx.stream>>>(n, q, tmp.get(), n, colscale_dev, dst, n);
-    SCGBM_LAUNCH_CHECK();
-  };
-  if (d > 0) {
-    SCGBM_REQUIRE(a->U && a->V && a->D, "sim: U, V, D required when d > 0");
-    SCGBM_CUDA(cudaMemcpyAsync(Dd.get(), a->D, d * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
-    conv(a->U, I, d, Dd.get(), Ud.get());
-    conv(a->V, J, d, nullptr, Vf.get());
-  }
-  conv(a->alpha, I, 1, nullptr, al.get());
-  conv(a->beta, J, 1, nullptr, be.get());
-  DevBuf<unsigned long long> nsat(1);
-  nsat.zero(ctx.stream);
-  dim3 grid((unsigned)std::min<int64_t>(ceil_div(a->ld, 256), 64), (unsigned)J);
-  SCGBM_REQUIRE(J <= 2147483647ll, "sim: J too large for one launch");
-  // blockIdx.y is limited to 65535: loop over column slabs
-  const int64_t slab = 65535;
-  for (int64_t j0 = 0; j0 < J; j0 += slab) {
-    const int64_t jc = std::min(slab, J - j0);
-    dim3 g(grid.x, (unsigned)jc);
-    const size_t sm = std::max(d, 1) * sizeof(float);
-#define SIM_LAUNCH(T)                                                                              \
-    sim_counts_kernel<T><<<g, 256, sm, ctx.stream>>>(I, J, a->ld, a->j_offset + j0, d, Ud.get(),    \
-        Vf.get() + j0, al.get(), be.get() + j0, a->nb_theta, a->seed, (T*)Y_dev + j0 * a->ld, nsat.get())
-    switch (a->out_dtype) {
-      case SCGBM_U8: SIM_LAUNCH(uint8_t); break;
-      case SCGBM_U16: SIM_LAUNCH(uint16_t); break;
-      case SCGBM_F32: SIM_LAUNCH(float); break;
-      case SCGBM_I32: SIM_LAUNCH(int32_t); break;
-      default: throw Error(SCGBM_ERR_INVALID, "sim: unsupported out_dtype");
-    }
-#undef SIM_LAUNCH
-    SCGBM_LAUNCH_CHECK();
-  }
-  unsigned long long h = 0;
-  SCGBM_CUDA(cudaMemcpyAsync(&h, nsat.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
-  ctx.sync();
-  if (n_saturated) *n_saturated = (int64_t)h;
-}
-
 }  // namespace scgbm

@@ -26,6 +26,9 @@ struct XDesc {
   const float* rowscale = nullptr;  // ldI x nbatch or null (multi-batch X0 only)
   const Factor16* A16 = nullptr;    // genes (side 0) and cells (side 1) for the tcgen05 passes, or null
   const Factor16* B16 = nullptr;
+  // fp64 factors of an unclamped low-rank X = U diag(d) V^T (null otherwise): rows whose |x| grows beyond what the
+  // 22-bit tensor-core eta resolves to 1e-5 are re-summed exactly from these (pass_rowsum_tc)
+  const double* U64 = nullptr; const double* d64 = nullptr; const double* V64 = nullptr;
 };
 
 struct PassGeom {
@@ -39,7 +42,17 @@ struct EtaWs {
   DevBuf<double> scal_part;  // [ctas][4]
   DevBuf<double> scal;       // [4]: sum_w, sum_ylogw, max_w, spare
   DevBuf<float> gmask;       // exp(beta) masked to one batch (multi-batch row sums on tcgen05)
+  DevBuf<int> row_flag;      // ldI: genes whose row sum is redone in fp64 (max |x| over the row >= kExactRowX)
+  DevBuf<unsigned long long> exact_rows;   // [1] running count of such rows (diagnostic)
+  DevBuf<int> exact_list;    // [1 + cap]: count, then the flagged genes in ascending order
+  DevBuf<double> exact_part; // [nbatch][cap][cell chunks] fixed-order partial sums
 };
+
+// |x| beyond which a gene's row sum S_i = sum_j exp(beta_j + x_ij) is recomputed in fp64: the tensor-core eta carries
+// 22 bits, i.e. an absolute error of |x| 2^-22 (x some cancellation), and alpha_i = log rs_i - log S_i inherits it
+// undiluted when a few large entries dominate the row (sparse genes the fit drives to |x| ~ 50): measured at
+// 20 000 genes, alpha error 4.6e-6 for rows with max |x| < 16, up to 3.4e-5 beyond (tolerance 1e-5).
+constexpr float kExactRowX = 12.0f;
 
 // S[i,k] = sum_{j in batch k} g_j * exp(X_ij)      (R/fit.R:129)   -> S (ldI x nbatch, fp64)
 void pass_rowsum(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* g_col, double* S);
@@ -61,7 +74,9 @@ bool eta_tc_supported(const PassGeom& g, const XDesc& x, int y_storage /* -1: pa
 // side 0 = genes [hi|hi|lo], side 1 = cells [hi|lo|hi]; value = U[r,k] * d[k] * rs[r]
 void stage_factor16(Ctx& ctx, Factor16& f, int64_t n_real, int64_t ld, int M, int side, const double* U,
                     const double* d, const float* rs);
-void pass_rowsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* g_col, double* S);
+// beta64 (J, fp64) together with x.U64/d64/V64 enables the exact re-summation of extreme rows (kExactRowX)
+void pass_rowsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* g_col, double* S,
+                    const double* beta64 = nullptr);
 // f_row / g_col must be zero padded by 128 entries beyond ldI / ldJ (whole 128-wide tiles are read)
 void pass_colsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* f_row, double* C);
 // alpha/beta (fp64) and this rank's row sums of Y close the objective:

@@ -29,17 +29,26 @@ namespace scgbm {
 // ---------------------------------------------------------------------------------
 // factor staging: fp64 (ld x M) [* d] [* rowscale] -> fp16 rows [ld_pad][Kp], three sections
 // ---------------------------------------------------------------------------------
+// out[0] = max |v| (float bits), out[2] = max over rows of the row's 2-norm (float bits): |x_ij| <= |a_i| |b_j|
+// bounds eta from below for the exp-underflow guard of the fused pass (ll_const_kernel)
 __global__ void factor_absmax_kernel(int64_t n_real, int64_t ld, int M, const double* __restrict__ U,
                                      const double* __restrict__ d, const float* __restrict__ rs, int* __restrict__ out) {
-  float m = 0.0f;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_real * M; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(idx / n_real);
-    const int64_t r = idx % n_real;
-    const double v = U[(int64_t)k * ld + r] * (d ? d[k] : 1.0) * (rs ? (double)rs[r] : 1.0);
-    m = fmaxf(m, fabsf((float)v));
+  float m = 0.0f, nm = 0.0f;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_real; r += (int64_t)gridDim.x * blockDim.x) {
+    const double rsv = rs ? (double)rs[r] : 1.0;
+    double n2 = 0.0;
+    for (int k = 0; k < M; ++k) {
+      const double v = U[(int64_t)k * ld + r] * (d ? d[k] : 1.0) * rsv;
+      m = fmaxf(m, fabsf((float)v));
+      n2 += v * v;
+    }
+    nm = fmaxf(nm, (float)sqrt(n2) * 1.0000002f);     // rounded up: this is a bound
   }
-  m = warp_max(m);
-  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out, __float_as_int(m));
+  m = warp_max(m); nm = warp_max(nm);
+  if ((threadIdx.x & 31) == 0) {
+    if (m > 0.0f) atomicMax(out, __float_as_int(m));
+    if (nm > 0.0f) atomicMax(out + 2, __float_as_int(nm));
+  }
 }
 
 // side 0 (genes): [hi | hi | lo];  side 1 (cells): [hi | lo | hi];  rows >= n_real and columns >= M are zero
@@ -74,11 +83,11 @@ void stage_factor16(Ctx& ctx, Factor16& f, int64_t n_real, int64_t ld, int M, in
   f.Kp = (int)round_up(3 * f.Mp, 64);
   f.rows_pad = round_up(ld, 128);
   if (f.data.n < f.rows_pad * f.Kp) f.data.alloc(f.rows_pad * f.Kp);
-  if (f.meta.n < 2) f.meta.alloc(2);
+  if (f.meta.n < 4) f.meta.alloc(4);      // [0] max |v| (bits), [1] 1 / scale, [2] max row 2-norm (bits)
   int* absmax = reinterpret_cast<int*>(f.meta.get());
   ProfScope ps(ctx.prof, SCGBM_K_MISC, 2);
-  SCGBM_CUDA(cudaMemsetAsync(absmax, 0, sizeof(int), ctx.stream));
-  factor_absmax_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_real * M, 256), 2048), 256, 0, ctx.stream>>>(n_real, ld, M, U, d, rs, absmax);
+  SCGBM_CUDA(cudaMemsetAsync(absmax, 0, 4 * sizeof(int), ctx.stream));
+  factor_absmax_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_real, 256), 2048), 256, 0, ctx.stream>>>(n_real, ld, M, U, d, rs, absmax);
   factor_stage16_kernel<<<(unsigned)ceil_div(f.rows_pad * f.Mp, 256), 256, 0, ctx.stream>>>(
       n_real, f.rows_pad, ld, M, f.Mp, f.Kp, side, U, d, rs, absmax, f.data.get(), f.meta.get() + 1);
   SCGBM_LAUNCH_CHECK();
@@ -124,7 +133,7 @@ struct FusedTcParams {
 // Ritz block, known before this pass) into a second TMEM accumulator; every two tiles four drain warps
 // (12-15, one per TMEM lane quarter) fold that accumulator into fp64 registers (same 128-step drain as prod_tc_kernel).  The warm SVD's
 // first pass G^T Q0 then needs no pass over the planes at all.  Requires one unit per cell tile.
-template <typename YT, bool CLAMP, bool MB, bool PROD>
+template <typename YT, bool CLAMP, bool MB, bool PROD, bool PK>
 __global__ void __launch_bounds__(PROD ? FT_NT_PROD : FT_NT, 1)
 fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_constant__ CUtensorMap map_genes,
                 const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_hi,
@@ -303,13 +312,16 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
           pwait(&r_full[rb], (fph >> rb) & 1u, p.ns_prod, true);     // all 8 epilogue warps wrote (and proxy-fenced) their part
           fph ^= 1u << rb;
           uint8_t* rt = r_buf + rb * FT_R_BYTES;
-          if (lead) {
+          auto ship = [&]() {
             tc::tma_store_2d(&map_hi, rt, gene0, ct * FT_CELLS);
             tc::tma_store_2d(&map_lo, rt + FT_CELLS * 128, gene0, ct * FT_CELLS);
             tc::tma_store_commit();
             tc::tma_store_wait_read<1>();                    // the previous tile's store has drained the other buffer
             if (ntile >= 1) tc::mbar_arrive(&r_free[rb ^ 1]);
-          }
+          };
+          // store first, product UMMAs second: issuing the UMMAs ahead of the store was measured slower
+          // (26.3 vs 24.9 ms per pass at 1M cells) -- the store queue is the critical resource of this kernel
+          if (lead) ship();
           if (PROD) {
             const uint32_t st = ntile % FT_NOP;
             if ((g & 1) == 0) { pwait(&p_empty[pb], ((peph >> pb) & 1u) ^ 1u, 0, true); peph ^= 1u << pb; }
@@ -403,6 +415,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
     float mw = 0.0f;
     uint32_t ys = 0, yph = 0, db = 0, rb = 0;
     uint32_t dph = 0, rfph = 0;   // phase bits per buffer (bit masks: indexed arrays would live in local memory)
+    const uint32_t y_s = tc::smem_u32(y_buf), r_s = tc::smem_u32(r_buf), f_s = tc::smem_u32(f_ring);
     for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
       int ct, gt0, ngt;
       unit_info(unit, ct, gt0, ngt);
@@ -418,8 +431,10 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
         dph ^= 1u << db;
         tc::mbar_wait(&y_full[ys], yph);
         tc::fence_after_sync();
-        const uint8_t* yt = y_buf + ys * p.y_stage_bytes;
-        uint8_t* rt = r_buf + rb * FT_R_BYTES;
+        // 32-bit shared addresses: LDS / STS instead of generic loads and stores (tc_common.cuh)
+        const uint32_t yt = y_s + ys * (uint32_t)p.y_stage_bytes + (uint32_t)row * (sizeof(YT) == 2 ? 128u : 64u);
+        const uint32_t rt = r_s + rb * (uint32_t)FT_R_BYTES + (uint32_t)row * 128u;
+        const uint32_t ft = f_s + ys * (uint32_t)(FT_GENES * 4);
         // Without the rider: issue every load of the tile's two chunks first (TMEM, Y from smem, f_i broadcast),
         // wait once, hand the TMEM buffer back to the MMA warp, then do the arithmetic (168 registers).
         // With it the kernel launches 512 threads at 128 registers and ptxas keeps the epilogue near that
@@ -434,16 +449,16 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
           tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + db * FT_GENES + col, xr2[c]);
           if (sizeof(YT) == 2) {
             const int q0 = col >> 3;                   // 16-byte chunk index (8 genes each)
-            yv[c][0] = *reinterpret_cast<const uint4*>(yt + row * 128 + (((q0) ^ (row & 7)) << 4));
-            yv[c][1] = *reinterpret_cast<const uint4*>(yt + row * 128 + (((q0 + 1) ^ (row & 7)) << 4));
+            yv[c][0] = tc::lds128(yt + (uint32_t)(((q0) ^ (row & 7)) << 4));
+            yv[c][1] = tc::lds128(yt + (uint32_t)(((q0 + 1) ^ (row & 7)) << 4));
           } else {
-            yv[c][0] = *reinterpret_cast<const uint4*>(yt + row * 64 + col);
+            yv[c][0] = tc::lds128(yt + (uint32_t)col);
             yv[c][1] = make_uint4(0u, 0u, 0u, 0u);
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             fv[c][k] = MB ? __ldg(reinterpret_cast<const float4*>(p.f_row + boff + gene0 + col) + k)
-                          : *reinterpret_cast<const float4*>(f_ring + ys * FT_GENES + col + 4 * k);
+                          : tc::lds128f(ft + (uint32_t)((col + 4 * k) * 4));
         };
         constexpr bool SEQ = PROD;
         if constexpr (!SEQ) {
@@ -461,6 +476,75 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
             if (c == 1) { tc::fence_before_sync(); tc::mbar_arrive(&d_empty[db]); }
           }
           uint32_t (&xr)[16] = xr2[c];
+          uint32_t hp[8], lp[8];
+          if constexpr (PK) {
+            // ---- packed form: two entries per FADD2 / FMUL2 / FFMA2, ~9 issued instructions per entry ----
+            // count -> float by a byte permute into the mantissa of 2^(23+k) (PRMT) and one packed subtraction;
+            // w = ex2(x L2E) (f_i g_j); clipping (R/fit.R:145) is deferred to the rare chunk that needs it.
+            const tc::f32x2 L2 = tc::pk2(L2E, L2E), G2 = tc::pk2(gj, gj), NM2 = tc::pk2(-magic, -magic);
+            tc::f32x2 SW2 = tc::pk2(0.0f, 0.0f), SY2 = tc::pk2(0.0f, 0.0f);
+            float cm = 0.0f;
+            const uint32_t yw[8] = {yv[c][0].x, yv[c][0].y, yv[c][0].z, yv[c][0].w, yv[c][1].x, yv[c][1].y, yv[c][1].z, yv[c][1].w};
+            const float fs[16] = {fv[c][0].x, fv[c][0].y, fv[c][0].z, fv[c][0].w, fv[c][1].x, fv[c][1].y, fv[c][1].z, fv[c][1].w,
+                                  fv[c][2].x, fv[c][2].y, fv[c][2].z, fv[c][2].w, fv[c][3].x, fv[c][3].y, fv[c][3].z, fv[c][3].w};
+            auto ybits = [&](int k) -> uint32_t {     // float bits of 2^(23+k) + count k of the chunk
+              if (sizeof(YT) == 2) return __byte_perm(yw[k >> 1], magic_bits, (k & 1) ? 0x7632u : 0x7610u);
+              return __byte_perm(yw[k >> 2], magic_bits, 0x7640u | (uint32_t)(k & 3));
+            };
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) {
+              float x0 = __uint_as_float(xr[2 * pp]), x1 = __uint_as_float(xr[2 * pp + 1]);
+              if (MB && CLAMP && p.rowscale) {                          // X0 with batches: per (gene, batch) scaling, R/fit.R:117
+                x0 *= __ldg(p.rowscale + boff + gene0 + col + 2 * pp);
+                x1 *= __ldg(p.rowscale + boff + gene0 + col + 2 * pp + 1);
+              }
+              if (CLAMP) {                                              // R/fit.R:119-120
+                x0 = fminf(fmaxf(x0, -clampv), clampv); x1 = fminf(fmaxf(x1, -clampv), clampv);
+              }
+              if (CLAMP || MB) { xr[2 * pp] = __float_as_uint(x0); xr[2 * pp + 1] = __float_as_uint(x1); }
+              const tc::f32x2 X2 = tc::pk2(x0, x1);
+              const tc::f32x2 Y2 = tc::add2(tc::pk2(__uint_as_float(ybits(2 * pp)), __uint_as_float(ybits(2 * pp + 1))), NM2);
+              float t0, t1;
+              tc::upk2(tc::mul2(X2, L2), t0, t1);
+              const tc::f32x2 W2 = tc::mul2(tc::pk2(ex2_approx(t0), ex2_approx(t1)), tc::mul2(tc::pk2(fs[2 * pp], fs[2 * pp + 1]), G2));
+              float w0, w1;
+              tc::upk2(W2, w0, w1);
+              cm = tc::max3(cm, w0, w1);
+              SW2 = tc::add2(SW2, W2);
+              SY2 = tc::fma2(Y2, X2, SY2);
+              float r0, r1;
+              tc::upk2(tc::sub2(Y2, W2), r0, r1);                       // 2^k (Y - W)
+              tc::split_f16x2_pair(r0, r1, hp[pp], lp[pp]);
+            }
+            float s0, s1, u0, u1;
+            tc::upk2(SW2, s0, s1); tc::upk2(SY2, u0, u1);
+            float tsw = s0 + s1;
+            const float tsyl = u0 + u1;
+            double corr = 0.0;
+            if (cm > maxYs) {   // rare: some W of this chunk exceeds max.Y -- redo it entry by entry with the clip;
+                                // clipped entries take log(max.Y) instead of eta in the objective (R/fit.R:145,151)
+              tsw = 0.0f;
+              float rr[16];
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const float xs = __uint_as_float(xr[k]);
+                const float yk = __uint_as_float(ybits(k)) - magic;
+                const float w = ex2_approx(xs * L2E) * (fs[k] * gj);    // same value as above
+                const float wc = fminf(w, maxYs);
+                tsw += wc;
+                rr[k] = yk - wc;
+                if (w > maxYs && yk != 0.0f) {
+                  const float lw = xs * inv + (__ldg(p.la_row + boff + gene0 + col + k) + lbj);
+                  corr += (double)(yk * inv_rs) * (double)(p.log_maxY - lw);
+                }
+              }
+#pragma unroll
+              for (int pp = 0; pp < 8; ++pp) tc::split_f16x2_pair(rr[2 * pp], rr[2 * pp + 1], hp[pp], lp[pp]);
+            }
+            sw64 += (double)tsw;
+            syl64 += (double)tsyl * (double)(inv * inv_rs) + corr;
+            mw = fmaxf(mw, fminf(cm, maxYs));
+          } else {
           float y[16];
           if (sizeof(YT) == 2) {
             const uint32_t w[8] = {yv[c][0].x, yv[c][0].y, yv[c][0].z, yv[c][0].w, yv[c][1].x, yv[c][1].y, yv[c][1].z, yv[c][1].w};
@@ -533,7 +617,6 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
           syl64 += (double)tsyl * (double)(inv * inv_rs) + corr;
           mw = fmaxf(mw, fminf(cm, maxYs));
           // fp16 planes, 16 genes = 32 bytes per plane: two 16-byte swizzled chunks
-          uint32_t hp[8], lp[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const __half2 h2 = __floats2half2_rn(r[2 * k], r[2 * k + 1]);
@@ -542,17 +625,17 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
             hp[k] = *reinterpret_cast<const uint32_t*>(&h2);
             lp[k] = *reinterpret_cast<const uint32_t*>(&l2);
           }
+          }   // !PK
           if (c == 0) {   // the store that read r_buf[rb] two tiles ago must have drained it
             tc::mbar_wait(&r_free[rb], ((rfph >> rb) & 1u) ^ 1u);
             rfph ^= 1u << rb;
           }
           const int q0 = col >> 3;
-          uint8_t* rh = rt + row * 128;
-          uint8_t* rl = rt + FT_CELLS * 128 + row * 128;
-          *reinterpret_cast<uint4*>(rh + (((q0) ^ (row & 7)) << 4)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-          *reinterpret_cast<uint4*>(rh + (((q0 + 1) ^ (row & 7)) << 4)) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
-          *reinterpret_cast<uint4*>(rl + (((q0) ^ (row & 7)) << 4)) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
-          *reinterpret_cast<uint4*>(rl + (((q0 + 1) ^ (row & 7)) << 4)) = make_uint4(lp[4], lp[5], lp[6], lp[7]);
+          const uint32_t o0 = (uint32_t)(((q0) ^ (row & 7)) << 4), o1 = (uint32_t)(((q0 + 1) ^ (row & 7)) << 4);
+          tc::sts128(rt + o0, hp[0], hp[1], hp[2], hp[3]);
+          tc::sts128(rt + o1, hp[4], hp[5], hp[6], hp[7]);
+          tc::sts128(rt + FT_CELLS * 128 + o0, lp[0], lp[1], lp[2], lp[3]);
+          tc::sts128(rt + FT_CELLS * 128 + o1, lp[4], lp[5], lp[6], lp[7]);
         }
         // the Y stage is free again
         tc::mbar_arrive(&y_empty[ys]);
@@ -589,11 +672,12 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
 //           log(0) = -Inf for a non-zero count and takes the NaN/Inf branch (R/fit.R:152-157).  The tensor-core
 //           pass sums Y * eta directly and would never see that, so the caller re-runs such an iteration on the
 //           CUDA-core pass, which restates the underflow entry by entry (eta_pass.cu).  The test is a bound:
-//           eta_ij >= min(alpha) + min(beta) - xb with |x_ij| <= xb = M * max|a| * max|b| (8 for the clamped X0).
+//           eta_ij >= min(alpha) + min(beta) - xb with |x_ij| <= xb = max_i |a_i|_2 * max_j |b_j|_2 (Cauchy-Schwarz
+//           on the staged factor rows; 8 for the clamped X0).
 __global__ void __launch_bounds__(1024)
 ll_const_kernel(int64_t I, const double* __restrict__ alpha, const double* __restrict__ rs, int64_t J,
                 const double* __restrict__ beta, const double* __restrict__ cs, double* __restrict__ out,
-                int xM, int xclamp, const int* __restrict__ amax_a, const int* __restrict__ amax_b) {
+                int xM, int xclamp, const int* __restrict__ meta_a, const int* __restrict__ meta_b) {
   __shared__ double red[1024];
   __shared__ double rmin[1024];
   double s = 0.0, mn_a = 0.0, mn_b = 1e300;
@@ -619,7 +703,7 @@ ll_const_kernel(int64_t I, const double* __restrict__ alpha, const double* __res
   if (threadIdx.x == 0) {
     double xb = 0.0;
     if (xM > 0) {
-      xb = (double)xM * (double)__int_as_float(*amax_a) * (double)__int_as_float(*amax_b);
+      xb = (double)__int_as_float(meta_a[2]) * (double)__int_as_float(meta_b[2]);
       if (xclamp) xb = fmin(xb, 8.0);
     }
     const double lo = red[0] + rmin[0] - xb;
@@ -643,6 +727,8 @@ struct RowsumTcParams {
   const float* lane_scale;  // per-lane multiplier of x before the clamp (X0 with batches) or null
   const float* inv_a; const float* inv_b;
   double* row_part;     // [chunk][4][ldI]
+  int* row_flag;        // [ldI] or null: set when some |x| of the lane's row reaches flag_x (rows re-summed in fp64)
+  float flag_x;
 };
 
 template <bool CLAMP>
@@ -737,12 +823,14 @@ rowsum_tc_kernel(const __grid_constant__ CUtensorMap map_genes, const __grid_con
     const float inv = __ldg(p.inv_a) * __ldg(p.inv_b);
     const float L_hi = 1.4426950216293335f * inv, L_lo = 1.9259629911e-08f * inv;
     const float clampv = 8.0f / inv;
+    const float flagv = p.flag_x / inv;                  // in the scaled units of the accumulator
     uint32_t db = 0;
     uint32_t dph = 0;
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
       int gt, ct0, nct;
       unit_info(unit, gt, ct0, nct);
       double s64 = 0.0;
+      float xm = 0.0f;                                   // max |x| of this lane's row over the unit (ALU pipe; the kernel is MUFU-bound)
       float lsc = 1.0f;
       if (CLAMP && p.lane_scale) {
         const int64_t lr = (int64_t)gt * RT_TILE + row;
@@ -770,6 +858,7 @@ rowsum_tc_kernel(const __grid_constant__ CUtensorMap map_genes, const __grid_con
           for (int k = 0; k < 16; ++k) {
             float xs = __uint_as_float(xr[k]);
             if (CLAMP) xs = fminf(fmaxf(xs * lsc, -clampv), clampv);
+            else xm = fmaxf(xm, fabsf(xs));
             ts = fmaf(ex2_approx(fmaf(xs, L_lo, xs * L_hi)), gj[k], ts);
           }
         }
@@ -781,7 +870,10 @@ rowsum_tc_kernel(const __grid_constant__ CUtensorMap map_genes, const __grid_con
       // the four column quarters of a gene meet in the fixed-order second stage: [chunk][quarter][ldI]
       const int chunk = unit / p.n_gene_tiles;
       const int64_t gene = (int64_t)gt * RT_TILE + row;
-      if (gene < p.ldI) p.row_part[((int64_t)chunk * 4 + ch) * p.ldI + gene] = s64;
+      if (gene < p.ldI) {
+        p.row_part[((int64_t)chunk * 4 + ch) * p.ldI + gene] = s64;
+        if (!CLAMP && p.row_flag && xm >= flagv) p.row_flag[gene] = 1;    // idempotent: any unit may raise it
+      }
     }
   }
   tc::fence_before_sync();
@@ -883,11 +975,13 @@ void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const
   }
   {
     ProfScope ps(ctx.prof, SCGBM_K_FUSED, 1);
-#define LAUNCH_FUSED(YT, CL, MBF, PR)                                                                                          \
+#define LAUNCH_FUSED_PK(YT, CL, MBF, PR, PKF)                                                                                       \
   do {                                                                                                                         \
-    SCGBM_CUDA(cudaFuncSetAttribute(fused_tc_kernel<YT, CL, MBF, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
-    fused_tc_kernel<YT, CL, MBF, PR><<<grid, PR ? FT_NT_PROD : FT_NT, smem_bytes, ctx.stream>>>(mc, mg, my, mh, ml, mo, p);                        \
+    SCGBM_CUDA(cudaFuncSetAttribute(fused_tc_kernel<YT, CL, MBF, PR, PKF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
+    fused_tc_kernel<YT, CL, MBF, PR, PKF><<<grid, PR ? FT_NT_PROD : FT_NT, smem_bytes, ctx.stream>>>(mc, mg, my, mh, ml, mo, p);   \
   } while (0)
+#define LAUNCH_FUSED(YT, CL, MBF, PR)                                                                       \
+  do { if (packed) LAUNCH_FUSED_PK(YT, CL, MBF, PR, true); else LAUNCH_FUSED_PK(YT, CL, MBF, PR, false); } while (0)
 #define LAUNCH_FUSED_Y(YT)                                                                                   \
   do {                                                                                                       \
     if (do_prod) { if (mb) LAUNCH_FUSED(YT, false, true, true); else LAUNCH_FUSED(YT, false, false, true); } \
@@ -895,9 +989,16 @@ void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const
     else { if (x.clamp) LAUNCH_FUSED(YT, true, false, false); else LAUNCH_FUSED(YT, false, false, false); }  \
   } while (0)
     const bool mb = g.nbatch > 1;
+    // packed-fp32 epilogue (FADD2/FMUL2/FFMA2, PRMT count unpack, FHADD split: 9 instead of ~20 issued instructions
+    // per entry).  Measured at 20k x 1M: 23.5 vs 23.9 ms without the rider, but 25.9 vs 25.3 ms with it (the rider's
+    // instantiation is register-capped at 128 and the 64-bit pairs cost it spills/moves), so each instantiation gets
+    // the form that is faster for it; SCGBM_FUSED_PACKED=0|1 forces one (A/B measurements).
+    static const char* pk_env = getenv("SCGBM_FUSED_PACKED");
+    const bool packed = pk_env ? pk_env[0] != '0' : !do_prod;
     if (ybytes == 2) LAUNCH_FUSED_Y(uint16_t); else LAUNCH_FUSED_Y(uint8_t);
 #undef LAUNCH_FUSED_Y
 #undef LAUNCH_FUSED
+#undef LAUNCH_FUSED_PK
     SCGBM_LAUNCH_CHECK();
   }
   {
@@ -917,7 +1018,7 @@ void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const
 // colsum: lanes = cells, streamed = genes, colfac = exp(alpha).  colfac is zero padded to whole tiles.
 static void lane_sums_tc(Ctx& ctx, EtaWs& ws, const Factor16& lanes, const Factor16& streamed, int64_t ld_lanes,
                          int64_t n_streamed, const float* colfac, bool clamp, double* out, int prof_class,
-                         const float* lane_scale = nullptr) {
+                         const float* lane_scale = nullptr, int* row_flag = nullptr) {
   RowsumTcParams p;
   memset(&p, 0, sizeof(p));
   p.J = n_streamed; p.ldI = ld_lanes;
@@ -928,6 +1029,7 @@ static void lane_sums_tc(Ctx& ctx, EtaWs& ws, const Factor16& lanes, const Facto
   p.cell_tiles_per_chunk = (int)ceil_div(p.n_cell_tiles, chunks);
   p.n_chunks = (int)ceil_div(p.n_cell_tiles, p.cell_tiles_per_chunk);
   p.g_col = colfac; p.lane_scale = lane_scale;
+  p.row_flag = row_flag; p.flag_x = kExactRowX;
   p.inv_a = lanes.meta.get() + 1; p.inv_b = streamed.meta.get() + 1;
   const int64_t n = ld_lanes;
   if (ws.row_part.n < (int64_t)p.n_chunks * 4 * n) ws.row_part.alloc((int64_t)p.n_chunks * 4 * n);
@@ -957,23 +1059,132 @@ __global__ void mask_batch_kernel(int64_t J, int64_t n_pad, const float* __restr
   if (j < n_pad) out[j] = (j < J && batch[j] == k) ? g[j] : 0.0f;
 }
 
-void pass_rowsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* g_col, double* S) {
-  if (g.nbatch == 1) {
-    lane_sums_tc(ctx, ws, *x.A16, *x.B16, g.ldI, g.J, g_col, x.clamp != 0, S, SCGBM_K_ROWSUM);
-    return;
+// ---- exact re-summation of the flagged genes (eta_pass.cuh kExactRowX) -------------------------------------
+// S[i, k] = sum_{j in batch k} exp(beta_j + x_ij) in fp64, x_ij = sum_m U_im d_m V_jm from the fp64 factors.
+// (1) one CTA compacts the flags into a gene list (ascending, so the work layout is deterministic);
+// (2) CTAs (cell chunk, slot lane) accumulate fixed-order partial sums part[k][slot][chunk];
+// (3) one thread per (slot, batch) adds the chunks in order and overwrites S.  No host round trip.
+constexpr int XR_CAP = 2048;      // genes per call; further flagged genes keep their tensor-core sum
+constexpr int XR_CHUNK = 4096;    // cells per partial sum
+constexpr int XR_LANES = 32;      // gridDim.y: slots are strided over these
+
+__global__ void __launch_bounds__(1024)
+exact_rows_compact_kernel(int64_t I, const int* __restrict__ row_flag, int* __restrict__ list /* [0] = count, then genes */,
+                          unsigned long long* __restrict__ total) {
+  __shared__ int wsum[32];
+  __shared__ int base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int64_t i0 = 0; i0 < I; i0 += 1024) {
+    const int64_t i = i0 + threadIdx.x;
+    const int f = (i < I && row_flag[i]) ? 1 : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wsum[w] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int q = 0; q < w; ++q) off += wsum[q];
+    off += __popc(bal & ((1u << lane) - 1u));
+    if (f && off < XR_CAP) list[1 + off] = (int)i;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int q = 0; q < 32; ++q) t += wsum[q]; base += t; }
+    __syncthreads();
   }
-  // S_ik = sum over the cells of batch k: one pass per batch with exp(beta) masked to that batch
-  // (and, for the X0 form, the batch's row scaling as a per-lane factor)
-  const int64_t n_pad = g.ldJ + 128;
-  if (ws.gmask.n < n_pad) ws.gmask.alloc(n_pad);
-  for (int k = 0; k < g.nbatch; ++k) {
-    {
-      ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
-      mask_batch_kernel<<<(unsigned)ceil_div(n_pad, 256), 256, 0, ctx.stream>>>(g.J, n_pad, g_col, g.batch, k, ws.gmask.get());
-      SCGBM_LAUNCH_CHECK();
+  if (threadIdx.x == 0) {
+    const int n = base < XR_CAP ? base : XR_CAP;
+    list[0] = n;
+    atomicAdd(total, (unsigned long long)n);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+exact_rows_partial_kernel(int64_t ldI, int64_t J, int64_t ldJ, int M, const double* __restrict__ U,
+                          const double* __restrict__ d, const double* __restrict__ V, const double* __restrict__ beta,
+                          const int32_t* __restrict__ batch, int nbatch, const int* __restrict__ list, int nchunks,
+                          double* __restrict__ part /* [nbatch][XR_CAP][nchunks] */) {
+  const int count = list[0];
+  __shared__ double a_s[64];
+  __shared__ double red[8];
+  const int64_t j0 = (int64_t)blockIdx.x * XR_CHUNK;
+  for (int slot = blockIdx.y; slot < count; slot += gridDim.y) {
+    const int64_t i = list[1 + slot];
+    __syncthreads();
+    if (threadIdx.x < M) a_s[threadIdx.x] = U[(int64_t)threadIdx.x * ldI + i] * d[threadIdx.x];
+    __syncthreads();
+    for (int k = 0; k < nbatch; ++k) {
+      double s = 0.0;
+      for (int t = threadIdx.x; t < XR_CHUNK; t += 256) {      // fixed cell -> thread assignment
+        const int64_t j = j0 + t;
+        if (j >= J || (batch && batch[j] != k)) continue;
+        double x = 0.0;
+        for (int m = 0; m < M; ++m) x = fma(a_s[m], V[(int64_t)m * ldJ + j], x);
+        s += exp(beta[j] + x);
+      }
+      s = warp_sum(s);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double tsum = 0.0;
+        for (int w = 0; w < 8; ++w) tsum += red[w];
+        part[((int64_t)k * XR_CAP + slot) * nchunks + blockIdx.x] = tsum;
+      }
+      __syncthreads();
     }
-    lane_sums_tc(ctx, ws, *x.A16, *x.B16, g.ldI, g.J, ws.gmask.get(), x.clamp != 0, S + (int64_t)k * g.ldI, SCGBM_K_ROWSUM,
-                 x.rowscale ? x.rowscale + (int64_t)k * g.ldI : nullptr);
+  }
+}
+
+__global__ void exact_rows_finish_kernel(int64_t ldI, int nbatch, const int* __restrict__ list, int nchunks,
+                                         const double* __restrict__ part, double* __restrict__ S) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int count = list[0];
+  if (idx >= count * nbatch) return;
+  const int slot = idx % count, k = idx / count;
+  const double* p = part + ((int64_t)k * XR_CAP + slot) * nchunks;
+  double s = 0.0;
+  for (int c = 0; c < nchunks; ++c) s += p[c];
+  S[(int64_t)k * ldI + list[1 + slot]] = s;
+}
+
+void pass_rowsum_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const float* g_col, double* S,
+                    const double* beta64) {
+  static const bool no_exact = getenv("SCGBM_NO_EXACT_ROWS") != nullptr;      // experiments
+  const bool exact = !no_exact && beta64 && x.U64 && x.d64 && x.V64 && !x.clamp && x.M >= 1 && x.M <= 64;
+  int* flag = nullptr;
+  if (exact) {
+    if (ws.row_flag.n < g.ldI) ws.row_flag.alloc(g.ldI);
+    if (ws.exact_rows.n < 1) { ws.exact_rows.alloc(1); ws.exact_rows.zero(ctx.stream); }
+    ws.row_flag.zero(ctx.stream);
+    flag = ws.row_flag.get();
+  }
+  if (g.nbatch == 1) {
+    lane_sums_tc(ctx, ws, *x.A16, *x.B16, g.ldI, g.J, g_col, x.clamp != 0, S, SCGBM_K_ROWSUM, nullptr, flag);
+  } else {
+    // S_ik = sum over the cells of batch k: one pass per batch with exp(beta) masked to that batch
+    // (and, for the X0 form, the batch's row scaling as a per-lane factor)
+    const int64_t n_pad = g.ldJ + 128;
+    if (ws.gmask.n < n_pad) ws.gmask.alloc(n_pad);
+    for (int k = 0; k < g.nbatch; ++k) {
+      {
+        ProfScope ps(ctx.prof, SCGBM_K_MISC, 1);
+        mask_batch_kernel<<<(unsigned)ceil_div(n_pad, 256), 256, 0, ctx.stream>>>(g.J, n_pad, g_col, g.batch, k, ws.gmask.get());
+        SCGBM_LAUNCH_CHECK();
+      }
+      lane_sums_tc(ctx, ws, *x.A16, *x.B16, g.ldI, g.J, ws.gmask.get(), x.clamp != 0, S + (int64_t)k * g.ldI, SCGBM_K_ROWSUM,
+                   x.rowscale ? x.rowscale + (int64_t)k * g.ldI : nullptr, flag);
+    }
+  }
+  if (exact) {
+    const int nchunks = (int)ceil_div(g.J, XR_CHUNK);
+    if (ws.exact_list.n < 1 + XR_CAP) ws.exact_list.alloc(1 + XR_CAP);
+    const int64_t need = (int64_t)g.nbatch * XR_CAP * nchunks;
+    if (ws.exact_part.n < need) ws.exact_part.alloc(need);
+    ProfScope ps(ctx.prof, SCGBM_K_ROWSUM, 3);
+    exact_rows_compact_kernel<<<1, 1024, 0, ctx.stream>>>(g.I, flag, ws.exact_list.get(), ws.exact_rows.get());
+    exact_rows_partial_kernel<<<dim3((unsigned)nchunks, XR_LANES), 256, 0, ctx.stream>>>(
+        g.ldI, g.J, g.ldJ, x.M, x.U64, x.d64, x.V64, beta64, g.batch, g.nbatch, ws.exact_list.get(), nchunks, ws.exact_part.get());
+    exact_rows_finish_kernel<<<(unsigned)ceil_div((int64_t)XR_CAP * g.nbatch, 256), 256, 0, ctx.stream>>>(
+        g.ldI, g.nbatch, ws.exact_list.get(), nchunks, ws.exact_part.get(), S);
+    SCGBM_LAUNCH_CHECK();
   }
 }
 

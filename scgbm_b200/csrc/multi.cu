@@ -162,7 +162,7 @@ void fit_multi_impl(const scgbm_fit_args* a, scgbm_fit_out* out) {
   out->n_obj = o0.n_obj; out->n_iter = o0.n_iter; out->hit_max_iter = o0.hit_max_iter;
   out->y_storage = o0.y_storage; out->max_Y = o0.max_Y; out->x_rank = o0.x_rank;
   out->svd_unconverged = o0.svd_unconverged; out->svd_worst_est = o0.svd_worst_est;
-  out->underflow_reruns = o0.underflow_reruns;
+  out->underflow_reruns = o0.underflow_reruns; out->exact_rows = o0.exact_rows;
   out->prof = o0.prof;
   for (int r = 1; r < n; ++r) {                      // host<->device traffic of the whole call
     out->prof.h2d_bytes += rb[r].o.prof.h2d_bytes;

@@ -176,6 +176,75 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 
+// ---- explicit shared-memory accesses ------------------------------------------------------------------------
+// Pointers derived from the dynamic shared-memory base by run-time offsets lose their address space: the compiler
+// then emits GENERIC loads/stores (LD.E / ST.E: 64-bit address arithmetic, L1TEX "long scoreboard" latency) where
+// LDS / STS would do.  These take a 32-bit shared address (smem_u32) instead.
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// ---- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 do two fp32 operations per issued instruction) ----------
+// The epilogues of the eta kernels are bound by instruction issue, not by a pipe: every pair of entries handled
+// by one packed instruction frees an issue slot.  A pair lives in a 64-bit register {lo, hi}.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {      // FMNMX3
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// (hi, lo) fp16 pair split of two fp32 values r0, r1:  h2 = rn_f16x2(r1, r0);  l2 = rn_f16x2(r1 - h.hi, r0 - h.lo).
+// The differences come from the mixed-precision add (FHADD: f16 + f32 -> f32, exact operands, one rounding),
+// fed with the sign-flipped halves, so no conversion back to fp32 is needed: 5 instructions per pair.
+__device__ __forceinline__ void split_f16x2_pair(float r0, float r1, uint32_t& h2, uint32_t& l2) {
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(r1), "f"(r0));
+  const uint32_t nh = h2 ^ 0x80008000u;
+  unsigned short n0, n1;
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(n0), "=h"(n1) : "r"(nh));
+  float d0, d1;
+  asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(d0) : "h"(n0), "f"(r0));
+  asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(d1) : "h"(n1), "f"(r1));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(d1), "f"(d0));
+}
+
 // ---- UMMA descriptors (cute/arch/mma_sm100_desc.hpp bit layout) -----------------------
 // shared-memory matrix descriptor, 128-byte swizzle, version 1 (Blackwell):
 //   K-major : rows of 128 B (K contiguous), 8-row groups SBO bytes apart; LBO unused (1)

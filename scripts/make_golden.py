@@ -40,7 +40,7 @@ def knife_free_fit(Y, M, **kw):
 def fit_fields(ref):
     return dict(LL=ref["_LL"], accepted=ref["_accepted"], obj=ref["obj"], n_iter=ref["_n_iter"],
                 hit_max_iter=ref["_hit_max_iter"], alpha=ref["alpha"], beta=ref["beta"], U=ref["U"], V=ref["V"],
-                D=ref["D"], scores=ref["scores"])
+                D=ref["D"], scores=ref["scores"], alpha_xmax=ref["_alpha_xmax"])
 
 
 def small():

@@ -39,7 +39,7 @@ def test_struct_layouts_match_header():
 #include <stdio.h>
 #include "scgbm.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(scgbm_profile), sizeof(scgbm_fit_args),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(scgbm_simdata_args), sizeof(scgbm_simdata_out), sizeof(scgbm_cci_args), sizeof(scgbm_profile), sizeof(scgbm_fit_args),
          sizeof(scgbm_fit_out), sizeof(scgbm_se_args), sizeof(scgbm_se_out), sizeof(scgbm_proj_args),
          sizeof(scgbm_proj_out), sizeof(scgbm_sim_args), sizeof(scgbm_tsvd_args), sizeof(scgbm_tsvd_out),
          sizeof(scgbm_eval_args), sizeof(scgbm_eval_out), sizeof(scgbm_prod_args), sizeof(scgbm_prod_out));
@@ -48,7 +48,7 @@ int main(void) {
         open(os.path.join(d, "t.c"), "w").write(prog)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
         sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
-    mine = [C.sizeof(t) for t in (L.Profile, L.FitArgs, L.FitOut, L.SeArgs, L.SeOut, L.ProjArgs, L.ProjOut,
+    mine = [C.sizeof(t) for t in (L.SimDataArgs, L.SimDataOut, L.CciArgs, L.Profile, L.FitArgs, L.FitOut, L.SeArgs, L.SeOut, L.ProjArgs, L.ProjOut,
                                   L.SimArgs, L.TsvdArgs, L.TsvdOut, L.EvalArgs, L.EvalOut, L.ProdArgs, L.ProdOut)]
     assert mine == sizes
 

@@ -63,6 +63,7 @@ def test_golden_fixture():
     out = gbm_sc(G["Y"], int(G["M"]), infer_beta=bool(G["infer_beta"]), max_iter=int(G["max_iter"]), diagnostics=True)
     ref = {k: G[k] for k in ("alpha", "beta", "U", "V", "D", "scores", "obj")}
     ref["_LL"] = G["LL"]; ref["_accepted"] = G["accepted"]; ref["_n_iter"] = int(G["n_iter"])
+    ref["_alpha_xmax"] = G["alpha_xmax"]
     # the fixture is knife-edge free (scripts/make_golden.py): alpha, beta, U, V, D, scores are all compared
     assert assert_fit_parity(ref, out, check_W=False) == "full"
     assert bool(out["_hit_max_iter"]) == bool(G["hit_max_iter"])

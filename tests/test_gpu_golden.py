@@ -23,6 +23,7 @@ def _fixture(name):
     G = np.load(os.path.join(GOLD, name))
     ref = {k: G[k] for k in ("alpha", "beta", "U", "V", "D", "scores", "obj")}
     ref["_LL"] = G["LL"]; ref["_accepted"] = G["accepted"]; ref["_n_iter"] = int(G["n_iter"])
+    ref["_alpha_xmax"] = G["alpha_xmax"]
     Y = sim_counts_exact_rows(**ast.literal_eval(str(G["gen"])))
     assert digest(Y) == str(G["y_digest"]), "the generator no longer reproduces the fixture's count matrix"
     return G, ref, Y

