@@ -241,6 +241,8 @@ typedef struct scgbm_proj_out {
   int8_t* fail;       /* J: 1 = GLM failed, row left at zero (R/fit.R:251-261) */
   int32_t* iters;     /* J or NULL: IRLS iterations used             */
   scgbm_profile prof;
+  double* rowsum_full; /* I_full or NULL: rowSums(Y) of ALL genes over this call's cells (R/fit.R:217), computed from
+                        * the same upload so that the host never has to sweep the I x J matrix itself */
 } scgbm_proj_out;
 
 int scgbm_project(const scgbm_proj_args* args, scgbm_proj_out* out);
@@ -434,6 +436,11 @@ int scgbm_dbg_eval(const scgbm_eval_args* args, scgbm_eval_out* out);
 /* symmetric eigen-decomposition on device (Jacobi): A (n x n, col-major) ->
  * eigenvalues descending in w, eigenvectors in the columns of A. */
 int scgbm_dbg_eigh(double* A, double* w, int32_t n, int32_t device);
+
+/* streaming rates of this GPU for two read : write mixes, plain coalesced kernels over 1 GiB streams:
+ * gbs[0] = copy (1 read : 1 write, what MEASURED_PEAKS.json's hbm_gbs is), gbs[1] = 1 read : 2 writes (the traffic
+ * pattern of the fused likelihood pass: Y in, two residual planes out).  bench.py reports both next to the roofline. */
+int scgbm_dbg_membench(int32_t device, double gbs[2]);
 
 #ifdef __cplusplus
 }

@@ -93,7 +93,7 @@ class ProjArgs(C.Structure):
 
 class ProjOut(C.Structure):
     _fields_ = [("beta", C.c_void_p), ("scores", C.c_void_p), ("se_scores", C.c_void_p),
-                ("fail", C.c_void_p), ("iters", C.c_void_p), ("prof", Profile)]
+                ("fail", C.c_void_p), ("iters", C.c_void_p), ("prof", Profile), ("rowsum_full", C.c_void_p)]
 
 
 class SimArgs(C.Structure):
@@ -168,7 +168,7 @@ EXPORTS = [
     "scgbm_host_alloc_pinned", "scgbm_host_free_pinned", "scgbm_flush_l2",
     "scgbm_comm_unique_id", "scgbm_comm_init_rank", "scgbm_comm_destroy", "scgbm_comm_allreduce_f64",
     "scgbm_last_error", "scgbm_device_count", "scgbm_version",
-    "scgbm_dbg_tsvd", "scgbm_dbg_eval", "scgbm_dbg_eigh", "scgbm_dbg_prod",
+    "scgbm_dbg_tsvd", "scgbm_dbg_eval", "scgbm_dbg_eigh", "scgbm_dbg_prod", "scgbm_dbg_membench",
 ]
 
 _lib = None
@@ -212,6 +212,7 @@ def load():
     lib.scgbm_dbg_prod.argtypes = [C.POINTER(ProdArgs), C.POINTER(ProdOut)]
     lib.scgbm_dbg_eval.argtypes = [C.POINTER(EvalArgs), C.POINTER(EvalOut)]
     lib.scgbm_dbg_eigh.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+    lib.scgbm_dbg_membench.argtypes = [C.c_int32, C.c_void_p]
     _lib = lib
     return lib
 

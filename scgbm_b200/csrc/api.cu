@@ -58,6 +58,32 @@ static void use_device(int device) {
   if (device >= 0) SCGBM_CUDA(cudaSetDevice(device));
 }
 
+// each thread: NR 16-byte streaming loads and NW 16-byte streaming stores per step, 4 steps in flight
+template <int NR, int NW>
+__global__ void __launch_bounds__(256) membench_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n_steps) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t s0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s0 < n_steps; s0 += 4 * stride) {
+    uint4 v[4][NR];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const size_t s = s0 + (size_t)u * stride;
+        v[u][r] = s < n_steps ? __ldcs(in + s + (size_t)r * n_steps) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t s = s0 + (size_t)u * stride;
+      if (s >= n_steps) continue;
+      uint4 a = v[u][0];
+#pragma unroll
+      for (int r = 1; r < NR; ++r) { a.x ^= v[u][r].x; a.y += v[u][r].y; }
+#pragma unroll
+      for (int w = 0; w < NW; ++w) __stcs(out + s + (size_t)w * n_steps, make_uint4(a.x + w, a.y, a.z, a.w));
+    }
+  }
+}
+
 extern "C" {
 
 int scgbm_fit(const scgbm_fit_args* args, scgbm_fit_out* out) {
@@ -160,6 +186,34 @@ int scgbm_device_count(void) {
   return n;
 }
 int scgbm_version(void) { return SCGBM_VERSION; }
+
+int scgbm_dbg_membench(int32_t device, double gbs[2]) {
+  return guarded([&] {
+    SCGBM_REQUIRE(gbs, "NULL out");
+    Ctx ctx(device, nullptr);
+    const size_t n_steps = (size_t)1 << 26;      // 1 GiB per stream
+    DevBuf<uint4> in((int64_t)n_steps), out((int64_t)n_steps * 2);
+    in.zero(ctx.stream);
+    cudaEvent_t a, b;
+    SCGBM_CUDA(cudaEventCreate(&a)); SCGBM_CUDA(cudaEventCreate(&b));
+    const int grid = ctx.num_sms * 8;
+    for (int which = 0; which < 2; ++which) {
+      float best = 1e30f;
+      for (int rep = 0; rep < 4; ++rep) {
+        SCGBM_CUDA(cudaEventRecord(a, ctx.stream));
+        if (which == 0) membench_kernel<1, 1><<<grid, 256, 0, ctx.stream>>>(in.get(), out.get(), n_steps);
+        else membench_kernel<1, 2><<<grid, 256, 0, ctx.stream>>>(in.get(), out.get(), n_steps);
+        SCGBM_CUDA(cudaEventRecord(b, ctx.stream));
+        SCGBM_CUDA(cudaEventSynchronize(b));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0) best = std::min(best, ms);
+      }
+      gbs[which] = (double)n_steps * 16.0 * (which == 0 ? 2.0 : 3.0) / (best * 1e-3) / 1e9;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+  });
+}
 
 int scgbm_dbg_tsvd(const scgbm_tsvd_args* args, scgbm_tsvd_out* out) { return guarded([&] { dbg_tsvd_impl(args, out); }); }
 int scgbm_dbg_prod(const scgbm_prod_args* args, scgbm_prod_out* out) { return guarded([&] { dbg_prod_impl(args, out); }); }

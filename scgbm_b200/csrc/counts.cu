@@ -123,9 +123,40 @@ static void pack_dispatch(Ctx& ctx, cudaStream_t s, int storage, int y_dtype, co
   }
 }
 
+// row sums over ALL source rows of a raw (caller-typed) column block: out[i] += sum_j in[j * ld + i]
+// (gbm.proj.parallel needs rowSums(Y) of every gene, R/fit.R:217, also of the genes its fit filters out)
+template <typename Tin>
+__global__ void __launch_bounds__(256)
+raw_rowsum_kernel(const Tin* __restrict__ in, int64_t ld_in, int64_t I_src, int64_t jc, int64_t cols_per_block,
+                  double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= I_src) return;
+  const int64_t ja = (int64_t)blockIdx.y * cols_per_block, jb = min(jc, ja + cols_per_block);
+  double s = 0.0;
+  for (int64_t j = ja; j < jb; ++j) {
+    const double v = (double)in[j * ld_in + i];
+    s += (v == v) ? v : 0.0;
+  }
+  if (s != 0.0) atomicAdd(&out[i], s);        // integer-valued sums: order-independent
+}
+
+static void raw_rowsum(cudaStream_t s, int y_dtype, const void* in, int64_t ld_in, int64_t I_src, int64_t jc, double* out) {
+  const int64_t cpb = 512;
+  dim3 grid((unsigned)ceil_div(I_src, 256), (unsigned)ceil_div(jc, cpb));
+  switch (y_dtype) {
+    case SCGBM_I32: raw_rowsum_kernel<int32_t><<<grid, 256, 0, s>>>((const int32_t*)in, ld_in, I_src, jc, cpb, out); break;
+    case SCGBM_F64: raw_rowsum_kernel<double><<<grid, 256, 0, s>>>((const double*)in, ld_in, I_src, jc, cpb, out); break;
+    case SCGBM_U8: raw_rowsum_kernel<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)in, ld_in, I_src, jc, cpb, out); break;
+    case SCGBM_U16: raw_rowsum_kernel<uint16_t><<<grid, 256, 0, s>>>((const uint16_t*)in, ld_in, I_src, jc, cpb, out); break;
+    case SCGBM_F32: raw_rowsum_kernel<float><<<grid, 256, 0, s>>>((const float*)in, ld_in, I_src, jc, cpb, out); break;
+    default: throw Error(SCGBM_ERR_INVALID, "unknown y_dtype");
+  }
+  SCGBM_LAUNCH_CHECK();
+}
+
 static void load_impl(Ctx& ctx, const void* Y, int y_dtype, int y_on_device, int64_t I_src, int64_t J,
                       int64_t ldY, const int64_t* rowmap_host, int64_t n_rows, const int32_t* batch_host,
-                      int nbatch, int storage_req, Counts& c) {
+                      int nbatch, int storage_req, Counts& c, double* full_rowsum = nullptr) {
   SCGBM_REQUIRE(Y != nullptr, "Y is NULL");
   SCGBM_REQUIRE(n_rows >= 1 && J >= 1, "Y must have at least one row and one column");
   SCGBM_REQUIRE(ldY >= I_src, "ldY < I");
@@ -169,8 +200,10 @@ static void load_impl(Ctx& ctx, const void* Y, int y_dtype, int y_on_device, int
     c.colsum.zero(ctx.stream);
     c.rowsum.zero(ctx.stream);
     st.zero(ctx.stream);
+    if (full_rowsum) SCGBM_CUDA(cudaMemsetAsync(full_rowsum, 0, (size_t)I_src * sizeof(double), ctx.stream));
     if (y_on_device) {
       ProfScope ps(ctx.prof, SCGBM_K_PACK, 1);
+      if (full_rowsum) raw_rowsum(ctx.stream, y_dtype, Y, ldY, I_src, J, full_rowsum);
       pack_dispatch(ctx, ctx.stream, storage, y_dtype, Y, ldY, rowmap.get(), n_rows, c.ld, J, c.data,
                     c.batch.get(), c.colsum.get(), c.rowsum.get(), st.get(), native ? 0 : 1);
     } else {
@@ -203,6 +236,7 @@ static void load_impl(Ctx& ctx, const void* Y, int y_dtype, int y_on_device, int
           SCGBM_CUDA(cudaStreamWaitEvent(ctx.stream, copied[k], 0));
           {
             ProfScope ps(ctx.prof, SCGBM_K_PACK, 1);
+            if (full_rowsum) raw_rowsum(ctx.stream, y_dtype, raw[k].get(), ldY, I_src, jc, full_rowsum);
             pack_dispatch(ctx, ctx.stream, storage, y_dtype, raw[k].get(), ldY, rowmap.get(), n_rows, c.ld, jc,
                           (uint8_t*)c.data + (size_t)j0 * c.ld * c.elem_bytes(),
                           c.batch.get() ? c.batch.get() + j0 : nullptr, c.colsum.get() + j0,
@@ -361,10 +395,10 @@ void load_counts(Ctx& ctx, const void* Y, int y_dtype, int y_on_device, int64_t 
 }
 
 void load_counts_rows(Ctx& ctx, const void* Y, int y_dtype, int y_on_device, int64_t I_full, int64_t J,
-                      int64_t ldY, const int64_t* ixs_host, int64_t Ik, Counts& c) {
+                      int64_t ldY, const int64_t* ixs_host, int64_t Ik, Counts& c, double* full_rowsum_dev) {
   for (int64_t r = 0; r < Ik; ++r)
     SCGBM_REQUIRE(ixs_host[r] >= 0 && ixs_host[r] < I_full, "ixs out of range");
-  load_impl(ctx, Y, y_dtype, y_on_device, I_full, J, ldY, ixs_host, Ik, nullptr, 1, SCGBM_STORE_AUTO, c);
+  load_impl(ctx, Y, y_dtype, y_on_device, I_full, J, ldY, ixs_host, Ik, nullptr, 1, SCGBM_STORE_AUTO, c, full_rowsum_dev);
 }
 
 }  // namespace scgbm

@@ -31,7 +31,9 @@ void load_counts_csc(Ctx& ctx, const int32_t* csc_i, const int64_t* csc_p, const
                      int64_t I, int64_t J, const int32_t* batch_host, int nbatch, int storage_req, Counts& c);
 
 // gather rows `ixs` of Y (all columns) into a packed Counts (projection path, R/fit.R:237)
+// full_rowsum_dev (I_full doubles, device, optional): row sums of ALL genes of Y (R/fit.R:217), from the same upload
 void load_counts_rows(Ctx& ctx, const void* Y, int y_dtype, int y_on_device, int64_t I_full,
-                      int64_t J, int64_t ldY, const int64_t* ixs_host, int64_t Ik, Counts& c);
+                      int64_t J, int64_t ldY, const int64_t* ixs_host, int64_t Ik, Counts& c,
+                      double* full_rowsum_dev = nullptr);
 
 }  // namespace scgbm

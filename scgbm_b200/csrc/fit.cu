@@ -13,7 +13,7 @@ namespace scgbm {
 enum { XK_ZERO = 0, XK_LOWRANK = 1, XK_X0 = 2 };
 
 // Ritz residual estimate at which the block-Krylov SVD stops.  irlba's own default is tol = 1e-5 (R/fit.R:115,323
-// call it with defaults [ext]); the looser 1e-4 of round 1 left the spans 1.4e-4 rad from the exact-SVD oracle at
+// call it with defaults [ext]); the looser 1e-4 of round 1 left the spans 1.4e-4 rad from an exact (LAPACK) SVD at
 // 20 000 genes x 2 000 cells (tests/golden/tall_*), outside the 1e-4 tolerance.
 constexpr double kDefaultSvdTol = 1e-5;
 

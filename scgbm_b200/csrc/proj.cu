@@ -206,14 +206,16 @@ void project_impl(const scgbm_proj_args* a, scgbm_proj_out* out) {
   const int PT = (int)ceil_div(T, WG_NT);
   SCGBM_REQUIRE(PT <= 9 && p <= WG_PMAX, "projection: M too large (M <= 63)");
   Counts Y;
+  DevBuf<double> rs_full;
+  if (out->rowsum_full) rs_full.alloc(a->I_full);
   if (a->Y) {
-    load_counts_rows(ctx, a->Y, a->y_dtype, a->y_on_device, a->I_full, J, a->ldY, a->ixs, Ik, Y);   // Y[ixs,]  R/fit.R:237
+    load_counts_rows(ctx, a->Y, a->y_dtype, a->y_on_device, a->I_full, J, a->ldY, a->ixs, Ik, Y, rs_full.get());   // Y[ixs,]  R/fit.R:237
   } else {
     // sparse Y: densify all genes on the device first (scatter), then gather the kept rows from there
     Counts full;
     load_counts_csc(ctx, a->csc_i, a->csc_p, a->csc_x, a->csc_x_dtype, a->I_full, J, nullptr, 1, SCGBM_STORE_AUTO, full);
     const int dt = full.storage == SCGBM_STORE_U8 ? SCGBM_U8 : (full.storage == SCGBM_STORE_U16 ? SCGBM_U16 : SCGBM_F32);
-    load_counts_rows(ctx, full.data, dt, 1, a->I_full, J, full.ld, a->ixs, Ik, Y);
+    load_counts_rows(ctx, full.data, dt, 1, a->I_full, J, full.ld, a->ixs, Ik, Y, rs_full.get());
     ctx.sync();
   }
   DevBuf<double> U(Ik * M), X(Ik * p), off(Ik), coef(J * p), se(J * p);
@@ -248,6 +250,7 @@ void project_impl(const scgbm_proj_args* a, scgbm_proj_out* out) {
   SCGBM_CUDA(cudaMemcpyAsync(out->se_scores, se.get() + J, J * M * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
   SCGBM_CUDA(cudaMemcpyAsync(out->fail, fail.get(), J * sizeof(int8_t), cudaMemcpyDeviceToHost, ctx.stream));
   if (out->iters) SCGBM_CUDA(cudaMemcpyAsync(out->iters, iters.get(), J * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx.stream));
+  if (out->rowsum_full) SCGBM_CUDA(cudaMemcpyAsync(out->rowsum_full, rs_full.get(), a->I_full * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
   SCGBM_CUDA(cudaEventRecord(ev1, ctx.stream));
   ctx.sync();
   ctx.prof.d2h_bytes += (double)J * (2 * M + 1) * sizeof(double);

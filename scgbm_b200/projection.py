@@ -31,11 +31,8 @@ def gbm_proj_parallel(Y, M, subsample=2000, min_counts=5, ncores=1, tol=1e-4, ma
     else:
         Yh, y_dt = _as_counts(Y)
         I, J = Yh.shape
-        rs = Yh.sum(axis=1, dtype=np.float64)
-    if comm is not None:
-        rs = comm.allreduce(rs)
-    with np.errstate(divide="ignore"):
-        alphas_full = np.log(rs)                                           # R/fit.R:217
+        rs = None      # rowSums(Y) (R/fit.R:217) comes back from scgbm_project, computed from the same upload:
+                       # sweeping a 20k x 1M host matrix with numpy would take longer than the whole projection
     if subsample_Y is not None:
         jxs = None
     elif np.ndim(subsample) == 0:                                            # R/fit.R:218-220
@@ -73,7 +70,15 @@ def gbm_proj_parallel(Y, M, subsample=2000, min_counts=5, ncores=1, tol=1e-4, ma
     o = L.ProjOut()
     o.beta = L.ptr(beta); o.scores = L.ptr(scores); o.se_scores = L.ptr(se_scores)
     o.fail = L.ptr(fail); o.iters = L.ptr(iters)
+    rs_dev = np.zeros(I) if rs is None else None
+    o.rowsum_full = L.ptr(rs_dev)
     L.check(lib.scgbm_project(C.byref(a), C.byref(o)))
+    if rs is None:
+        rs = rs_dev
+    if comm is not None:
+        rs = comm.allreduce(rs)
+    with np.errstate(divide="ignore"):
+        alphas_full = np.log(rs)                                           # R/fit.R:217
     out["se_scores"] = se_scores                                           # :268
     out["scores"] = scores                                                 # :269
     alpha = np.zeros(I)                                                    # :272

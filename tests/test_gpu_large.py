@@ -11,9 +11,8 @@ pytestmark = pytest.mark.gpu
 def _device_counts(I, J, d):
     import bench
     from scgbm_b200 import _lib as L
-    lib = L.load()
-    wl = bench.Workload(I, J, d)
-    return wl.host_slice(lib, L, 0, J, 0)
+    cfg = dict(bench.CONFIGS["c5p"], I=I, J=J, d=d, M=d)       # the benchmark's generator and parameters
+    return bench.host_counts(L.load(), L, cfg, 0, J, 0)[0]
 
 
 def test_large_fit_invariants_and_reproducibility():
