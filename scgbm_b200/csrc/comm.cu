@@ -57,6 +57,12 @@ static NcclApi& nccl() {
 struct Comm {
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0, device = 0;
+  // Several ranks inside ONE process (multi.cu: one host thread per GPU) share the CUDA driver's process-wide locks:
+  // a cudaFree on this GPU (implicit device synchronisation, lock held) issued while this GPU's NCCL kernel is
+  // still waiting for the peer's kernel deadlocks as soon as the peer's launch needs the same lock.  Such
+  // communicators therefore complete every collective before the caller goes on (one stream sync per all-reduce,
+  // a few tens of microseconds); ranks in separate processes keep the fully asynchronous path.
+  bool in_process = false;
 };
 
 Ctx::Ctx(int device_, Comm* comm_) : comm(comm_) {
@@ -89,11 +95,13 @@ void Ctx::allreduce_sum(double* dev, int64_t n) {
   if (!comm || nranks == 1 || n <= 0) return;
   ProfScope ps(prof, SCGBM_K_COMM, 1);
   SCGBM_NCCL(nccl().AllReduce(dev, dev, (size_t)n, ncclFloat64, ncclSum, comm->comm, stream));
+  if (comm->in_process) SCGBM_CUDA(cudaStreamSynchronize(stream));
 }
 void Ctx::allreduce_max(double* dev, int64_t n) {
   if (!comm || nranks == 1 || n <= 0) return;
   ProfScope ps(prof, SCGBM_K_COMM, 1);
   SCGBM_NCCL(nccl().AllReduce(dev, dev, (size_t)n, ncclFloat64, ncclMax, comm->comm, stream));
+  if (comm->in_process) SCGBM_CUDA(cudaStreamSynchronize(stream));
 }
 
 Comm* comm_create(const uint8_t* id, int nranks, int rank, int device) {
@@ -119,6 +127,7 @@ void comm_destroy(Comm* c) {
   if (c->comm && nccl().CommDestroy) nccl().CommDestroy(c->comm);
   delete c;
 }
+void comm_set_in_process(Comm* c) { if (c) c->in_process = true; }
 int comm_rank(Comm* c) { return c ? c->rank : 0; }
 int comm_nranks(Comm* c) { return c ? c->nranks : 1; }
 int comm_device(Comm* c) { return c ? c->device : -1; }

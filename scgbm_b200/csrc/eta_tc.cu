@@ -125,6 +125,9 @@ struct FusedTcParams {
   double* prod_out; int64_t prod_ld;  // J x prod_b, column-major
   const float* op_inv;                // device: 1 / operand scale
   uint32_t ns_prod, ns_mma, ns_drain; // back-off of the polling single-lane warps / UMMA issuer (0: spin) / drain warps
+  int dbg_no_store;                   // experiment (SCGBM_DBG_NO_STORE): keep everything but the residual-plane TMA stores --
+                                      // with the rider this IS an "implicit-W" product R^T Q (eta tile rebuilt, exp, fp16
+                                      // split in shared memory, second UMMA) that reads only Y; results are then wrong
 };
 
 // PROD: the tile that the epilogue just wrote to shared memory for the TMA store is, as it lies there
@@ -313,8 +316,10 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap map_cells, const __grid_cons
           fph ^= 1u << rb;
           uint8_t* rt = r_buf + rb * FT_R_BYTES;
           auto ship = [&]() {
-            tc::tma_store_2d(&map_hi, rt, gene0, ct * FT_CELLS);
-            tc::tma_store_2d(&map_lo, rt + FT_CELLS * 128, gene0, ct * FT_CELLS);
+            if (!p.dbg_no_store) {
+              tc::tma_store_2d(&map_hi, rt, gene0, ct * FT_CELLS);
+              tc::tma_store_2d(&map_lo, rt + FT_CELLS * 128, gene0, ct * FT_CELLS);
+            }
             tc::tma_store_commit();
             tc::tma_store_wait_read<1>();                    // the previous tile's store has drained the other buffer
             if (ntile >= 1) tc::mbar_arrive(&r_free[rb ^ 1]);
@@ -958,6 +963,8 @@ void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const
   // polling back-off (ns): measured flat between 64 and 400 for the single-lane warps, with or without a
   // back-off in the UMMA issuer; the drain warps poll once per ~3 us pair of tiles
   p.ns_prod = 64; p.ns_mma = 0; p.ns_drain = 400;
+  static const bool no_store = getenv("SCGBM_DBG_NO_STORE") != nullptr;
+  p.dbg_no_store = no_store ? 1 : 0;
   const int grid = std::min(p.n_units, ctx.num_sms);
   if (ws.scal_part.n < (int64_t)grid * 4) ws.scal_part.alloc((int64_t)grid * 4);
   p.scal_part = ws.scal_part.get();

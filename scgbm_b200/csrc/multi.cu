@@ -13,6 +13,7 @@ namespace scgbm {
 Comm* comm_create(const uint8_t* id, int nranks, int rank, int device);
 void comm_unique_id(uint8_t* id);
 void comm_destroy(Comm* c);
+void comm_set_in_process(Comm* c);
 void fit_impl(const scgbm_fit_args* a, scgbm_fit_out* out);
 void get_se_impl(const scgbm_se_args* a, scgbm_se_out* out);
 
@@ -66,6 +67,7 @@ static void run_ranks(const std::vector<int>& dev, F&& body) {
     try {
       SCGBM_CUDA(cudaSetDevice(dev[r]));
       comm = comm_create(id, n, r, dev[r]);
+      comm_set_in_process(comm);     // see comm.cu: collectives complete before the thread goes on
       body(r, comm);
     } catch (const Error& e) { err[r].status = e.status; err[r].msg = e.what(); }
     catch (const std::bad_alloc&) { err[r].status = SCGBM_ERR_NOMEM; err[r].msg = "host allocation failed"; }

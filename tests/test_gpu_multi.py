@@ -89,34 +89,72 @@ def test_n_ranks_match_one_gpu(world, kw):
     _check_against_one_gpu(res, one)
 
 
+def _in_child(target, *args, timeout=300):
+    """Runs target(q, *args) in a spawned child and returns what it put on the queue.  The in-process multi-GPU
+    driver blocks inside C code if it ever deadlocks, where no Python-level timeout can reach it: a child can be
+    killed, and a hang then costs `timeout` seconds instead of the whole GPU session."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=target, args=(q,) + args)
+    p.start()
+    try:
+        res = q.get(timeout=timeout)
+    except Exception:
+        p.kill(); p.join(30)
+        pytest.fail(f"{target.__name__} did not finish within {timeout} s (deadlock in the in-process multi-GPU driver?)")
+    p.join(60)
+    if isinstance(res, str):
+        pytest.fail(res)
+    return res
+
+
+def _one_caller_body(q, ngpu):
+    import traceback
+    try:
+        import scipy.sparse as sp
+        from scgbm_b200 import gbm_sc, get_se
+        from tests.util import principal_angle
+        Y = _data()
+        one = get_se(gbm_sc(Y, 8, diagnostics=True, max_iter=40))
+        many = gbm_sc(Y, 8, diagnostics=True, max_iter=40, ngpu=ngpu, quiet=True)
+        n = min(len(many["_LL"]), len(one["_LL"]))
+        np.testing.assert_array_equal(many["_accepted"][:n], one["_accepted"][:n])
+        np.testing.assert_allclose(many["_LL"][:n], one["_LL"][:n], rtol=1e-6)
+        np.testing.assert_allclose(many["alpha"], one["alpha"], atol=1e-5)
+        np.testing.assert_allclose(many["beta"], one["beta"], atol=1e-5)
+        assert principal_angle(many["U"], one["U"]) < 1e-4 and principal_angle(many["V"], one["V"]) < 1e-4
+        assert many["V"].shape == one["V"].shape and many["W"].shape == Y.shape
+        np.testing.assert_allclose(many["W"], one["W"], rtol=5e-4)
+        np.testing.assert_allclose(many["scores"], many["V"] * many["D"][None, :], rtol=1e-12)
+        se1 = get_se(many)
+        seN = get_se(many, ngpu=ngpu)            # cells split inside the library, gene-side Grams all-reduced
+        np.testing.assert_allclose(seN["se_scores"], se1["se_scores"], rtol=1e-9)
+        np.testing.assert_allclose(seN["se_loadings"], se1["se_loadings"], rtol=1e-9)
+        sparse = gbm_sc(sp.csc_matrix(Y.astype(np.float64)), 8, diagnostics=True, max_iter=40, ngpu=ngpu)
+        np.testing.assert_allclose(sparse["_LL"], many["_LL"], rtol=1e-12)
+        # an input error on one GPU's shard: the caller sees the originating rank's message (no deadlock)
+        from scgbm_b200 import RError
+        Yb = Y.astype(np.float64)
+        Yb[3, Y.shape[1] - 2] = -1.0
+        try:
+            gbm_sc(Yb, 8, ngpu=ngpu, max_iter=5)
+            raise AssertionError("negative count accepted")
+        except RError as e:
+            assert "negative" in str(e), str(e)
+        q.put(("ok", int(many["_n_iter"])))
+    except BaseException:
+        q.put(traceback.format_exc())
+
+
 @pytest.mark.parametrize("ngpu", [2, 4, 8])
 def test_one_caller_many_gpus(ngpu):
     """`gbm_sc(Y, M, ngpu=n)`: ONE call (the R user's calling convention, R/fit.R:52) drives n GPUs -- host threads
-    and NCCL ranks live inside the library.  Same fit as one GPU; with W, scores, get.se and sparse input."""
-    import scipy.sparse as sp
-    from scgbm_b200 import gbm_sc, get_se
-    from tests.util import principal_angle
+    and NCCL ranks live inside the library.  Same fit as one GPU; with W, scores, get.se, sparse input and the
+    error path."""
     _need_gpus(ngpu)
-    Y = _data()
-    one = get_se(gbm_sc(Y, 8, diagnostics=True, max_iter=40))
-    seen = []
-    many = gbm_sc(Y, 8, diagnostics=True, max_iter=40, ngpu=ngpu, quiet=True)
-    n = min(len(many["_LL"]), len(one["_LL"]))
-    np.testing.assert_array_equal(many["_accepted"][:n], one["_accepted"][:n])
-    np.testing.assert_allclose(many["_LL"][:n], one["_LL"][:n], rtol=1e-6)
-    np.testing.assert_allclose(many["alpha"], one["alpha"], atol=1e-5)
-    np.testing.assert_allclose(many["beta"], one["beta"], atol=1e-5)
-    assert principal_angle(many["U"], one["U"]) < 1e-4 and principal_angle(many["V"], one["V"]) < 1e-4
-    assert many["V"].shape == one["V"].shape and many["W"].shape == Y.shape
-    np.testing.assert_allclose(many["W"], one["W"], rtol=5e-4)
-    np.testing.assert_allclose(many["scores"], many["V"] * many["D"][None, :], rtol=1e-12)
-    se1 = get_se(many)
-    seN = get_se(many, ngpu=ngpu)            # cells split inside the library, gene-side Grams all-reduced
-    np.testing.assert_allclose(seN["se_scores"], se1["se_scores"], rtol=1e-9)
-    np.testing.assert_allclose(seN["se_loadings"], se1["se_loadings"], rtol=1e-9)
-    sparse = gbm_sc(sp.csc_matrix(Y.astype(np.float64)), 8, diagnostics=True, max_iter=40, ngpu=ngpu)
-    np.testing.assert_allclose(sparse["_LL"], many["_LL"], rtol=1e-12)
-    del seen
+    res = _in_child(_one_caller_body, ngpu)
+    assert res[0] == "ok"
 
 
 def _batch_worker(rank, world, port, q):
@@ -190,12 +228,6 @@ def test_error_on_one_rank_reaches_every_rank():
     res = _spawn(_bad_worker, 2, timeout=180)
     assert "negative" in res[1][1]
     assert "another rank" in res[0][1]
-    # and through the in-process driver the caller sees the originating rank's message
-    from scgbm_b200 import gbm_sc, RError
-    Y = _data().astype(np.float64)
-    Y[3, Y.shape[1] - 2] = -1.0
-    with pytest.raises(RError, match="negative"):
-        gbm_sc(Y, 8, ngpu=2, max_iter=5)
 
 
 def _proj_worker(rank, world, port, q):

