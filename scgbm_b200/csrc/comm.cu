@@ -2,6 +2,7 @@
 // (columns of Y) are sharded over ranks.  NCCL is loaded lazily with
 // dlopen so the single-GPU path has no NCCL dependency at all.
 #include <dlfcn.h>
+#include <condition_variable>
 #include <mutex>
 #include <nccl.h>   // types only; symbols are resolved with dlsym
 #include "common.cuh"
@@ -54,16 +55,41 @@ static NcclApi& nccl() {
     }                                                                                  \
   } while (0)
 
+// Several ranks inside ONE process (multi.cu: one host thread per GPU).  NCCL enables peer access between the GPUs,
+// and from then on a cudaFree on one GPU also waits for the kernels of its peers; a rank that frees a buffer while a
+// peer's all-reduce kernel is already spinning for this rank's (not yet launched) kernel dead-locks the process --
+// observed as a hang of gbm_sc(ngpu = 2) in round 2.  In-process communicators therefore (1) rendezvous on a host
+// barrier before every collective, so that no rank is inside a synchronising CUDA call while another has a
+// collective in flight, and (2) complete the collective before going on.  Ranks in separate processes keep the
+// fully asynchronous path.  A rank that fails marks the group aborted, which releases the others with an error.
+struct InprocGroup {
+  std::mutex m;
+  std::condition_variable cv;
+  int n = 0, count = 0;
+  uint64_t gen = 0;
+  bool aborted = false;
+  int finished = 0;                 // ranks that have left their body (successfully or not)
+};
+
 struct Comm {
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0, device = 0;
-  // Several ranks inside ONE process (multi.cu: one host thread per GPU) share the CUDA driver's process-wide locks:
-  // a cudaFree on this GPU (implicit device synchronisation, lock held) issued while this GPU's NCCL kernel is
-  // still waiting for the peer's kernel deadlocks as soon as the peer's launch needs the same lock.  Such
-  // communicators therefore complete every collective before the caller goes on (one stream sync per all-reduce,
-  // a few tens of microseconds); ranks in separate processes keep the fully asynchronous path.
-  bool in_process = false;
+  InprocGroup* group = nullptr;     // non-null: ranks are threads of this process
 };
+
+static void inproc_arrive(Comm* c) {
+  InprocGroup* g = c->group;
+  std::unique_lock<std::mutex> lk(g->m);
+  if (g->aborted) throw Error(SCGBM_ERR_CUDA, "another rank of this call failed; no rank proceeds");
+  const uint64_t gen0 = g->gen;
+  if (++g->count == g->n) {
+    g->count = 0; ++g->gen;
+    g->cv.notify_all();
+    return;
+  }
+  g->cv.wait(lk, [&] { return g->gen != gen0 || g->aborted; });
+  if (g->gen == gen0) throw Error(SCGBM_ERR_CUDA, "another rank of this call failed; no rank proceeds");
+}
 
 Ctx::Ctx(int device_, Comm* comm_) : comm(comm_) {
   int cur = 0;
@@ -93,15 +119,17 @@ Ctx::~Ctx() {
 
 void Ctx::allreduce_sum(double* dev, int64_t n) {
   if (!comm || nranks == 1 || n <= 0) return;
+  if (comm->group) inproc_arrive(comm);
   ProfScope ps(prof, SCGBM_K_COMM, 1);
   SCGBM_NCCL(nccl().AllReduce(dev, dev, (size_t)n, ncclFloat64, ncclSum, comm->comm, stream));
-  if (comm->in_process) SCGBM_CUDA(cudaStreamSynchronize(stream));
+  if (comm->group) SCGBM_CUDA(cudaStreamSynchronize(stream));
 }
 void Ctx::allreduce_max(double* dev, int64_t n) {
   if (!comm || nranks == 1 || n <= 0) return;
+  if (comm->group) inproc_arrive(comm);
   ProfScope ps(prof, SCGBM_K_COMM, 1);
   SCGBM_NCCL(nccl().AllReduce(dev, dev, (size_t)n, ncclFloat64, ncclMax, comm->comm, stream));
-  if (comm->in_process) SCGBM_CUDA(cudaStreamSynchronize(stream));
+  if (comm->group) SCGBM_CUDA(cudaStreamSynchronize(stream));
 }
 
 Comm* comm_create(const uint8_t* id, int nranks, int rank, int device) {
@@ -127,7 +155,22 @@ void comm_destroy(Comm* c) {
   if (c->comm && nccl().CommDestroy) nccl().CommDestroy(c->comm);
   delete c;
 }
-void comm_set_in_process(Comm* c) { if (c) c->in_process = true; }
+InprocGroup* inproc_group_create(int n) { InprocGroup* g = new InprocGroup(); g->n = n; return g; }
+void inproc_group_destroy(InprocGroup* g) { delete g; }
+void inproc_group_abort(InprocGroup* g) {
+  std::lock_guard<std::mutex> lk(g->m);
+  g->aborted = true;
+  g->cv.notify_all();
+}
+// every rank calls this once when it is done (or has failed): returns when all ranks are, i.e. when no collective
+// can be in flight any more and the communicators may be torn down
+void inproc_group_finish(InprocGroup* g) {
+  std::unique_lock<std::mutex> lk(g->m);
+  ++g->finished;
+  g->cv.notify_all();
+  g->cv.wait(lk, [&] { return g->finished >= g->n; });
+}
+void comm_set_in_process(Comm* c, InprocGroup* g) { if (c) c->group = g; }
 int comm_rank(Comm* c) { return c ? c->rank : 0; }
 int comm_nranks(Comm* c) { return c ? c->nranks : 1; }
 int comm_device(Comm* c) { return c ? c->device : -1; }

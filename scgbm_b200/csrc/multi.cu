@@ -13,7 +13,12 @@ namespace scgbm {
 Comm* comm_create(const uint8_t* id, int nranks, int rank, int device);
 void comm_unique_id(uint8_t* id);
 void comm_destroy(Comm* c);
-void comm_set_in_process(Comm* c);
+struct InprocGroup;
+InprocGroup* inproc_group_create(int n);
+void inproc_group_destroy(InprocGroup* g);
+void inproc_group_abort(InprocGroup* g);
+void inproc_group_finish(InprocGroup* g);
+void comm_set_in_process(Comm* c, InprocGroup* g);
 void fit_impl(const scgbm_fit_args* a, scgbm_fit_out* out);
 void get_se_impl(const scgbm_se_args* a, scgbm_se_out* out);
 
@@ -62,17 +67,24 @@ static void run_ranks(const std::vector<int>& dev, F&& body) {
   uint8_t id[SCGBM_UNIQUE_ID_BYTES];
   comm_unique_id(id);
   std::vector<RankError> err(n);
+  InprocGroup* group = inproc_group_create(n);
+  std::vector<Comm*> comms(n, nullptr);
   auto one = [&](int r) {
-    Comm* comm = nullptr;
     try {
       SCGBM_CUDA(cudaSetDevice(dev[r]));
-      comm = comm_create(id, n, r, dev[r]);
-      comm_set_in_process(comm);     // see comm.cu: collectives complete before the thread goes on
-      body(r, comm);
+      comms[r] = comm_create(id, n, r, dev[r]);
+      comm_set_in_process(comms[r], group); // see comm.cu: host rendezvous before, completion after every collective
+      body(r, comms[r]);
     } catch (const Error& e) { err[r].status = e.status; err[r].msg = e.what(); }
     catch (const std::bad_alloc&) { err[r].status = SCGBM_ERR_NOMEM; err[r].msg = "host allocation failed"; }
     catch (const std::exception& e) { err[r].status = SCGBM_ERR_CUDA; err[r].msg = e.what(); }
-    if (comm) comm_destroy(comm);
+    if (err[r].status) inproc_group_abort(group);     // release the ranks waiting for this one
+    // tear-down only when every rank has left its body: no collective can be in flight then, so the cross-device
+    // synchronisation of ncclCommDestroy's frees cannot wait for a kernel that needs a peer
+    inproc_group_finish(group);
+    cudaSetDevice(dev[r]);
+    cudaDeviceSynchronize();
+    if (comms[r]) { comm_destroy(comms[r]); comms[r] = nullptr; }
   };
   int cur = 0;
   cudaGetDevice(&cur);
@@ -80,6 +92,7 @@ static void run_ranks(const std::vector<int>& dev, F&& body) {
   for (int r = 1; r < n; ++r) th.emplace_back(one, r);
   one(0);
   for (auto& t : th) t.join();
+  inproc_group_destroy(group);
   cudaSetDevice(cur);
   // report the most informative failure: a rank's own message beats "rejected on another rank"
   int pick = -1;

@@ -326,11 +326,9 @@ template <int BP, bool TRANS>
 static void launch_tc(Ctx& ctx, const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mb, const TcParams& p) {
   using Cfg = TcCfg<BP>;
   auto kern = prod_tc_kernel<BP, TRANS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SCGBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  // a function attribute belongs to the DEVICE the call is made on: no process-wide "already set" flag (several
+  // GPUs may be driven from this one process, multi.cu)
+  SCGBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int grid = std::min(p.n_tiles, ctx.num_sms);
   kern<<<grid, TC_NT, Cfg::SMEM_BYTES, ctx.stream>>>(mh, ml, mb, p);
   SCGBM_LAUNCH_CHECK();

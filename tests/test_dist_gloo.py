@@ -120,6 +120,9 @@ def _proj_worker(rank, world, port, q):
             beta = np.ctypeslib.as_array(C.cast(o.beta, C.POINTER(C.c_double)), shape=(J,))
             sc = np.ctypeslib.as_array(C.cast(o.scores, C.POINTER(C.c_double)), shape=(M, J))
             se = np.ctypeslib.as_array(C.cast(o.se_scores, C.POINTER(C.c_double)), shape=(M, J))
+            if o.rowsum_full:                          # rowSums(Y) of all genes over this rank's cells (R/fit.R:217)
+                rsf = np.ctypeslib.as_array(C.cast(o.rowsum_full, C.POINTER(C.c_double)), shape=(a.I_full,))
+                rsf[:] = Yl.sum(axis=1)
             X = np.hstack([np.ones((Ik, 1)), U])
             for j in range(J):
                 coef, s, _, _ = O.poisson_glm_irls(X, Yl[ixs, j], alpha)
@@ -165,3 +168,54 @@ def test_sharded_projection_host_logic():
     np.testing.assert_allclose(np.concatenate([res[0][2], res[1][2]]), ref["beta"], atol=1e-10)
     np.testing.assert_allclose(np.vstack([res[0][3], res[1][3]]), ref["scores"], atol=1e-10)
     np.testing.assert_allclose(np.vstack([res[0][4], res[1][4]]), ref["se_scores"], rtol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------
+# Batch levels must be GLOBAL when the cells are sharded: a shard that lacks a level must not
+# re-number the levels it has.  Host logic of scgbm_b200/api.py::_batch_codes on two gloo ranks.
+# ---------------------------------------------------------------------------------------------
+def _levels_worker(rank, world, port, q):
+    import pickle
+    import torch
+    import torch.distributed as dist
+    from scgbm_b200.api import _batch_codes, RError
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        class GlooComm:
+            nranks = world
+
+            def allgather_bytes(self, payload):
+                out = [None] * world
+                dist.all_gather_object(out, payload)
+                return out
+        labels = np.array(["A", "B", "A", "B"]) if rank == 0 else np.array(["B", "B", "B"])      # rank 1 lacks level A
+        codes, nb = _batch_codes(labels, len(labels), comm=GlooComm())
+        num = np.array([3, 7, 3]) if rank == 0 else np.array([5, 5, 7])
+        ncodes, nnb = _batch_codes(num, 3, comm=GlooComm())
+        none_codes, none_nb = _batch_codes(None, 3, comm=GlooComm())
+        try:                        # batch given on one rank only: refused on both
+            _batch_codes(labels if rank == 0 else None, len(labels) if rank == 0 else 3, comm=GlooComm())
+            mixed = "accepted"
+        except RError as e:
+            mixed = str(e)
+        q.put((rank, codes.tolist(), nb, ncodes.tolist(), nnb, none_codes, none_nb, mixed))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_batch_levels_are_agreed_across_ranks():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_levels_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps: p.start()
+    res = sorted([q.get(timeout=120) for _ in ps], key=lambda r: r[0])
+    for p in ps:
+        p.join(60); assert p.exitcode == 0
+    assert res[0][1] == [1, 2, 1, 2] and res[1][1] == [2, 2, 2]        # B is level 2 on BOTH ranks
+    assert res[0][2] == res[1][2] == 2
+    assert res[0][3] == [1, 3, 1] and res[1][3] == [2, 2, 3] and res[0][4] == res[1][4] == 3
+    assert res[0][5] is None and res[1][5] is None and res[0][6] == res[1][6] == 1
+    assert "every rank or on none" in res[0][7] and "every rank or on none" in res[1][7]

@@ -21,14 +21,19 @@ def _need_gpus(n):
         pytest.skip(f"needs {n} GPUs, box has {have}")
 
 
-def _spawn(target, world, *args, timeout=600):
+def _spawn(target, world, *args, timeout=300):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     ps = [ctx.Process(target=target, args=(r, world, port, q) + args) for r in range(world)]
     for p in ps: p.start()
-    res = sorted([q.get(timeout=timeout) for _ in ps], key=lambda r: r[0])
+    try:
+        res = sorted([q.get(timeout=timeout) for _ in ps], key=lambda r: r[0])
+    except Exception:
+        for p in ps:
+            p.kill()
+        pytest.fail(f"{target.__name__}: the {world} ranks did not all report within {timeout} s")
     for p in ps:
         p.join(120); assert p.exitcode == 0
     return res
