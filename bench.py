@@ -365,7 +365,10 @@ def run_fit(name, cfg, args, R):
     NB = 3                      # extra, fully instrumented steps for the per-kernel breakdown (outside the timed region)
     a.M = M; a.max_iter = W + K + NB + 1; a.tol = 1e-4; a.min_iter = 10 ** 6; a.infer_beta = 0
     a.batch = None; a.nbatch = 1; a.return_W = 0; a.time_by_iter = 0
-    a.y_storage = L.STORE_U16; a.device = device; a.comm = R.comm.handle if R.comm else None
+    # AUTO: the library keeps the resident u16 matrix when some count exceeds 255 and repacks it as u8 otherwise
+    # (SCGBM_BENCH_STORAGE=u16 pins the two-byte format: A/B measurements)
+    a.y_storage = L.STORE_U16 if os.environ.get("SCGBM_BENCH_STORAGE", "auto") == "u16" else L.STORE_AUTO
+    a.device = device; a.comm = R.comm.handle if R.comm else None
     a.profile = 2; a.seed = 0   # timed region: CUDA events around the fused pass only (the roofline kernel)
     h = C.c_void_p()
     t0 = time.perf_counter()

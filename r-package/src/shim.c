@@ -123,7 +123,8 @@ SEXP scgbm_fit_R(SEXP Y, SEXP sM, SEXP sMaxIter, SEXP sTol, SEXP sMinIter, SEXP 
   if (o.svd_unconverged)
     warning("truncated SVD: %d call(s) stopped above the residual tolerance (worst estimate %.2e)", o.svd_unconverged, o.svd_worst_est);
 
-  const int n = (return_W ? 3 : 0) + 8 + (time_by_iter ? 1 : 0) + (keep ? 3 : 0);
+  /* V, D, U, loadings, alpha, beta, M, obj, scores = 9; W, I, J only with W; time; Xu, Xv, x.rank */
+  const int n = (return_W ? 3 : 0) + 9 + (time_by_iter ? 1 : 0) + (keep ? 3 : 0);
   SEXP out = PROTECT(allocVector(VECSXP, n)); np++;
   SEXP nm = PROTECT(allocVector(STRSXP, n)); np++;
   int k = 0;

@@ -394,6 +394,31 @@ void load_counts(Ctx& ctx, const void* Y, int y_dtype, int y_on_device, int64_t 
   load_impl(ctx, Y, y_dtype, y_on_device, I, J, ldY, nullptr, I, batch_host, nbatch, storage_req, c);
 }
 
+// u16 -> u8 in a fresh buffer (16 counts per thread); the caller has checked max(Y) <= 255
+__global__ void narrow_u16_u8_kernel(int64_t n16, const uint4* __restrict__ in, uint4* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n16) return;
+  const uint4 a = in[2 * i], b = in[2 * i + 1];
+  auto pk = [](uint32_t lo, uint32_t hi) {     // four u16 (two words) -> four u8
+    return (lo & 0xffu) | ((lo >> 8) & 0xff00u) | ((hi & 0xffu) << 16) | ((hi >> 16) << 24);
+  };
+  out[i] = make_uint4(pk(a.x, a.y), pk(a.z, a.w), pk(b.x, b.y), pk(b.z, b.w));
+}
+
+void narrow_counts_to_u8(Ctx& ctx, Counts& c) {
+  SCGBM_REQUIRE(c.storage == SCGBM_STORE_U16 && c.maxY <= 255.0, "narrow_counts_to_u8: not applicable");
+  const int64_t n = c.ld * c.J;                 // ld is a multiple of 64: n is a multiple of 16
+  DevBuf<uint8_t> dst(n);
+  ProfScope ps(ctx.prof, SCGBM_K_PACK, 1);
+  narrow_u16_u8_kernel<<<(unsigned)ceil_div(n / 16, 256), 256, 0, ctx.stream>>>(
+      n / 16, reinterpret_cast<const uint4*>(c.data), reinterpret_cast<uint4*>(dst.get()));
+  SCGBM_LAUNCH_CHECK();
+  SCGBM_CUDA(cudaStreamSynchronize(ctx.stream));
+  c.owned = std::move(dst);                     // releases the u16 copy if the library owned it (an aliased caller
+  c.data = c.owned.get();                       // buffer is left alone)
+  c.storage = SCGBM_STORE_U8;
+}
+
 void load_counts_rows(Ctx& ctx, const void* Y, int y_dtype, int y_on_device, int64_t I_full, int64_t J,
                       int64_t ldY, const int64_t* ixs_host, int64_t Ik, Counts& c, double* full_rowsum_dev) {
   for (int64_t r = 0; r < Ik; ++r)

@@ -30,6 +30,9 @@ void load_counts(Ctx& ctx, const void* Y, int y_dtype, int y_on_device, int64_t 
 void load_counts_csc(Ctx& ctx, const int32_t* csc_i, const int64_t* csc_p, const void* csc_x, int x_dtype,
                      int64_t I, int64_t J, const int32_t* batch_host, int nbatch, int storage_req, Counts& c);
 
+// AUTO storage, second step: max(Y) (over all ranks) turned out to be <= 255 -- repack the u16 matrix as u8 (s_Y = 1)
+void narrow_counts_to_u8(Ctx& ctx, Counts& c);
+
 // gather rows `ixs` of Y (all columns) into a packed Counts (projection path, R/fit.R:237)
 // full_rowsum_dev (I_full doubles, device, optional): row sums of ALL genes of Y (R/fit.R:217), from the same upload
 void load_counts_rows(Ctx& ctx, const void* Y, int y_dtype, int y_on_device, int64_t I_full,

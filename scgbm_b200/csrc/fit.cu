@@ -349,6 +349,14 @@ struct FitState {
     }
     J_total = (int64_t)llround(h[0]);
     maxY = h[1];
+    // AUTO picks the narrowest format the counts fit: u16 first (the maximum is only known after the pack), then
+    // u8 when the maximum over ALL ranks is <= 255 -- one byte per count less for the fused pass to read
+    // (SCGBM_AUTO_U8=0 keeps u16: A/B measurements)
+    static const bool auto_u8 = !(getenv("SCGBM_AUTO_U8") && getenv("SCGBM_AUTO_U8")[0] == '0');
+    if (auto_u8 && a.y_storage == SCGBM_STORE_AUTO && Y.storage == SCGBM_STORE_U16 && maxY <= 255.0) {
+      Y.maxY = std::min(Y.maxY, 255.0);
+      narrow_counts_to_u8(ctx, Y);
+    }
     SCGBM_REQUIRE(M >= 1, "M must be >= 1");
     SCGBM_REQUIRE(M <= std::min(I, J_total), "M must not exceed min(nrow(Y), ncol(Y))");
     SCGBM_REQUIRE(maxY > 0.0, "Count matrix Y is all zero");

@@ -62,22 +62,37 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// bounded spin: a protocol bug traps (visible CUDA error) instead of hanging the GPU box
+// Blocking wait.  mbarrier.try_wait SUSPENDS the thread in hardware until the phase completes or a time limit
+// expires; without a hint that limit is a few tens of cycles on B200, so a loop around the un-hinted form is a busy
+// poll: ncu (round 1, fused_tc_kernel with the product rider) counted 95 M try_wait executions per launch, i.e. ~40 %
+// of all issued warp instructions were poll-loop overhead of warps that had nothing to do -- issue slots taken from
+// the epilogue warps on the same schedulers (`__nanosleep` between the polls did not help: it returned after ~20
+// cycles).  With a suspend-time hint the waiter really sleeps and still wakes as soon as the phase flips.
+// A protocol bug traps after ~20 s (visible CUDA error) instead of hanging the GPU box.
+constexpr uint32_t kMbarSuspendNs = 1000000u;
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) { printf("scgbm: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  uint32_t tries = 0;
+  while (!mbar_try_wait_hint(bar, parity, kMbarSuspendNs)) {
+    if (++tries > 20000u) { printf("scgbm: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
   }
 }
-
-// same, for single-thread producer roles that may wait long: back off so that the spin does
-// not eat issue slots of the epilogue warps sharing the scheduler (ncu: 7 % of all issues)
+// same wait; the back-off argument of the polling era is kept in the signature (ignored: the hardware suspends)
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns = 64) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(ns);
-    if (++spins > (1u << 24)) { printf("scgbm: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
-  }
+  (void)ns;
+  mbar_wait(bar, parity);
 }
 
 // ---- TMA --------------------------------------------------------------------------

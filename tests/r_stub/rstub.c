@@ -126,10 +126,13 @@ int* INTEGER(SEXP s) { return (int*)typed(s, INTSXP, LGLSXP, "INTEGER"); }
 int* LOGICAL(SEXP s) { return (int*)typed(s, LGLSXP, LGLSXP, "LOGICAL"); }
 double* REAL(SEXP s) { return (double*)typed(s, REALSXP, REALSXP, "REAL"); }
 Rbyte* RAW(SEXP s) { return (Rbyte*)typed(s, RAWSXP, RAWSXP, "RAW"); }
-SEXP VECTOR_ELT(SEXP s, R_xlen_t i) { return ((SEXP*)typed(s, VECSXP, VECSXP, "VECTOR_ELT"))[i]; }
-SEXP SET_VECTOR_ELT(SEXP s, R_xlen_t i, SEXP v) { ((SEXP*)typed(s, VECSXP, VECSXP, "SET_VECTOR_ELT"))[i] = v; return v; }
-void SET_STRING_ELT(SEXP s, R_xlen_t i, SEXP v) { ((SEXP*)typed(s, STRSXP, STRSXP, "SET_STRING_ELT"))[i] = v; }
-SEXP STRING_ELT(SEXP s, R_xlen_t i) { return ((SEXP*)typed(s, STRSXP, STRSXP, "STRING_ELT"))[i]; }
+static void in_range(SEXP s, R_xlen_t i, const char* acc) {   /* R would corrupt memory here; the stand-in reports it */
+  if (i < 0 || i >= s->n) Rf_error("%s: index %ld outside a vector of length %ld", acc, (long)i, (long)s->n);
+}
+SEXP VECTOR_ELT(SEXP s, R_xlen_t i) { SEXP* p = (SEXP*)typed(s, VECSXP, VECSXP, "VECTOR_ELT"); in_range(s, i, "VECTOR_ELT"); return p[i]; }
+SEXP SET_VECTOR_ELT(SEXP s, R_xlen_t i, SEXP v) { SEXP* p = (SEXP*)typed(s, VECSXP, VECSXP, "SET_VECTOR_ELT"); in_range(s, i, "SET_VECTOR_ELT"); p[i] = v; return v; }
+void SET_STRING_ELT(SEXP s, R_xlen_t i, SEXP v) { SEXP* p = (SEXP*)typed(s, STRSXP, STRSXP, "SET_STRING_ELT"); in_range(s, i, "SET_STRING_ELT"); p[i] = v; }
+SEXP STRING_ELT(SEXP s, R_xlen_t i) { SEXP* p = (SEXP*)typed(s, STRSXP, STRSXP, "STRING_ELT"); in_range(s, i, "STRING_ELT"); return p[i]; }
 const char* R_CHAR(SEXP s) { return (const char*)typed(s, CHARSXP, SYMSXP, "CHAR"); }
 SEXP R_do_slot(SEXP obj, SEXP name) {
   SEXP v = Rf_getAttrib(obj, name);

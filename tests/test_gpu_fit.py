@@ -111,7 +111,10 @@ def test_storage_formats_agree(storage, dtype):
     out = gbm_sc(Y.astype(dtype), 4, diagnostics=True, max_iter=15, y_storage=storage)
     # u8 / u16 run the same tcgen05 kernels -> identical sums; f32 storage takes the CUDA-core kernels
     np.testing.assert_allclose(out["_LL"], base["_LL"], rtol=1e-12 if storage != 3 else 2e-7)
-    assert out["_y_storage"] == (storage if storage else 2)
+    assert out["_y_storage"] == (storage if storage else 1)      # AUTO: max(Y) <= 255 here -> u8 (s_Y = 1)
+    if storage == 0 and dtype is np.float64:
+        big = Y.astype(np.int32).copy(); big[0, 0] = 300              # one count above 255: AUTO stays at u16
+        assert gbm_sc(big, 4, diagnostics=True, max_iter=3)["_y_storage"] == 2
 
 
 def test_get_se_without_W():

@@ -64,6 +64,35 @@ def test_shim_compiles_and_raises_the_library_error_without_a_device(harness):
     assert "no CUDA device available" in r.stderr
 
 
+@pytest.mark.parametrize("sparse,return_W", [(False, True), (True, False)])
+def test_shim_list_assembly_without_a_device(tmp_path, sparse, return_W):
+    """The shim's marshalling executed on the CPU: harness + shim + R stand-in linked against a do-nothing stand-in
+    for libscgbm (tests/r_stub/fake_scgbm.c).  Catches what compiling alone cannot -- round 2 found the returned
+    list one element too short (a write past the end of `out`) this way."""
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = os.path.join(tmp_path, "harness_fake")
+    subprocess.check_call(["gcc", "-std=c11", "-O1", "-Wall", "-I", STUB, "-I", os.path.join(ROOT, "include"),
+                           os.path.join(STUB, "harness.c"), os.path.join(ROOT, "r-package", "src", "shim.c"),
+                           os.path.join(STUB, "rstub.c"), os.path.join(STUB, "fake_scgbm.c"), "-o", exe])
+    Y = np.random.default_rng(0).poisson(2.0, (6, 7))
+    _write_input(os.path.join(tmp_path, "in.bin"), Y, 2, 10, sparse, return_W)
+    r = subprocess.run([exe, "fit", os.path.join(tmp_path, "in.bin"), os.path.join(tmp_path, "out.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    names = [ln for ln in r.stdout.strip().split("\n") if not ln.startswith(("Iteration", "warnings="))]
+    base = ["V", "D", "U", "loadings", "alpha", "beta", "M"] + (["I", "J"] if return_W else []) + ["obj", "scores"]
+    assert names == (["W"] if return_W else []) + base + ([] if return_W else ["Xu", "Xv", "x.rank"])
+    out, se_s, se_l, pert = _read_output(os.path.join(tmp_path, "out.bin"), names)
+    assert out["D"][0] == 42.0 and out["obj"].tolist() == [-1.0, -0.5, -0.25] and out["M"][0] == 2
+    assert out["V"].shape == (7 * 2,) and out["U"].shape == (6 * 2,) and out["alpha"].shape == (6,)
+    assert se_s[0] == (1.0 if return_W else 2.0)          # get.se took the W path / the kept-factor path
+    assert pert[0] == 3.0 and pert.shape == (7 * 2 * 3,)
+    if not return_W:
+        assert out["x.rank"][0] == 2
+        r = subprocess.run([exe, "badcall", os.path.join(tmp_path, "in.bin"), os.path.join(tmp_path, "o2.bin")], capture_output=True, text=True)
+        assert r.returncode == 3 and "get.se needs out$W" in r.stderr
+
+
 def test_shim_sources_declare_every_registered_routine():
     """the .Call names used by r-package/R/*.R are exactly the routines registered in the shim"""
     import re
