@@ -354,3 +354,23 @@ def test_fused_product_rider_other_instantiations(variant, monkeypatch):
     np.testing.assert_array_equal(rider["_LL"], plain["_LL"])
     np.testing.assert_array_equal(rider["U"], plain["U"])
     np.testing.assert_array_equal(rider["V"], plain["V"])
+
+
+@pytest.mark.parametrize("rider", ["0", "force"])
+def test_packed_epilogue_agrees_with_the_plain_form(rider, monkeypatch):
+    """SCGBM_FUSED_PACKED=1 selects the packed-fp32 epilogue of the fused pass (FADD2 / FMUL2 / FFMA2; eta_tc.cu PK).
+    It rounds the residual differently in the last bit, nothing more: same accept / revert decisions, objective
+    within 1e-8 relative, alpha within 1e-7 -- far inside the parity tolerances; the default is the plain form."""
+    from scgbm_b200 import gbm_sc
+    from tests.util import principal_angle
+    Y = _sim(300, 700, 5, seed=21)
+    monkeypatch.setenv("SCGBM_FUSED_PROD", rider)
+    monkeypatch.setenv("SCGBM_FUSED_PACKED", "0")
+    plain = gbm_sc(Y, 5, diagnostics=True, max_iter=20)
+    monkeypatch.setenv("SCGBM_FUSED_PACKED", "1")
+    packed = gbm_sc(Y, 5, diagnostics=True, max_iter=20)
+    np.testing.assert_array_equal(packed["_accepted"], plain["_accepted"])
+    assert not np.array_equal(packed["_LL"], plain["_LL"])       # the knob really switched the kernel
+    np.testing.assert_allclose(packed["_LL"], plain["_LL"], rtol=1e-8)
+    np.testing.assert_allclose(packed["alpha"], plain["alpha"], atol=1e-7)
+    assert principal_angle(packed["U"], plain["U"]) < 1e-6

@@ -49,5 +49,11 @@ def test_large_fit_with_product_rider(monkeypatch):
     np.testing.assert_array_equal(a["_LL"], b["_LL"])
     np.testing.assert_array_equal(a["U"], b["U"])
     np.testing.assert_array_equal(a["_accepted"], plain["_accepted"])
-    np.testing.assert_array_equal(a["_LL"], plain["_LL"])       # the rider is bit-identical to the plain first pass
+    # The rider's product R^T Q0 is bit-identical to the plain first pass, so every factor and intercept is; the
+    # objective SCALAR is summed per CTA over the units that CTA happened to own, and the rider's launch owns whole
+    # cell tiles while the plain launch splits them into gene runs: the same fp64 terms in another grouping,
+    # i.e. equal to the last bit or two (observed 1.4e-16 relative in 2 of 10 iterations).
+    np.testing.assert_allclose(a["_LL"], plain["_LL"], rtol=1e-14, atol=0)
     np.testing.assert_array_equal(a["alpha"], plain["alpha"])
+    np.testing.assert_array_equal(a["U"], plain["U"])
+    np.testing.assert_array_equal(a["V"], plain["V"])

@@ -120,7 +120,8 @@ def test_shim_fit_get_se_and_cci_equal_the_ctypes_mirror(harness, sparse, return
                        timeout=300)
     assert r.returncode == 0, r.stderr
     lines = r.stdout.strip().split("\n")
-    names = [ln for ln in lines if not ln.startswith(("Iteration", "warnings="))]
+    # (NCCL prints its version banner on stdout when the in-process multi-GPU driver creates the communicators)
+    names = [ln for ln in lines if not ln.startswith(("Iteration", "warnings=", "NCCL version"))]
     base = ["V", "D", "U", "loadings", "alpha", "beta", "M"] + (["I", "J"] if return_W else []) + ["obj", "scores"]
     assert names == (["W"] if return_W else []) + base + ([] if return_W else ["Xu", "Xv", "x.rank"])   # R/fit.R:189-204,310
     out, se_s, se_l, pert = _read_output(os.path.join(d, "out.bin"), names)
