@@ -600,7 +600,10 @@ def run_proj(name, cfg, args, R):
     clocks = sampler.stop()
     wall = float(np.mean(walls))
     pp = out["_prof_proj"]
-    proj_ms = R.max(pp["ms"]["proj"])
+    # K9's device time: every kernel class of the scgbm_project call except the upload / pack of the counts (the
+    # tensor-core path spends it in the fused pass's product rider, class "fused"; the exact kernel in class "proj")
+    k9_ms = float(sum(v for k, v in pp["ms"].items() if k != "pack"))
+    proj_ms = R.max(k9_ms)
     fit_ms = out["_prof"]["total_ms"]
     Ik = len(out["_ixs"])
     sweeps = float(np.mean(out["_glm_iters"]))
@@ -613,13 +616,18 @@ def run_proj(name, cfg, args, R):
     return {
         "metric": "gbm_sc_subset_cells_per_sec", "value": J / (proj_ms * 1e-3), "unit": "cells/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": proj_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "dtype": "f32 (eta and products from fp16x2-split tcgen05 MMAs, fp32 exp; fp64 normal equations)" if out["_glm_method"] == "tcgen05" else "f64",
+        "data": "synthetic",
         "config": config_dict(name, cfg, world, {"subset": f"{S} explicit column indices ({blocks} blocks of {per})",
                                                  "genes_kept": int(Ik), "irls_sweeps_mean": sweeps, "glm_failures": fails}),
-        "roofline": {"bound": "tensor", "achieved": flops / (pp["ms"]["proj"] * 1e-3) / 1e12, "peak": None, "unit": "TFLOP/s",
-                     "frac": None, "traffic": None,
-                     "note": "K9 (proj_irls_kernel) forms the per-cell Khatri-Rao Grams as fp64 FMAs on the CUDA cores so that the "
-                             "IRLS iteration counts and the 1e-9 SE parity with fastglm hold; rank 0's launch"},
+        "roofline": {"bound": "tensor", "achieved": flops / (k9_ms * 1e-3) / 1e12, "peak": None, "unit": "TFLOP/s",
+                     "frac": None, "traffic": None, "glm_method": out["_glm_method"], "tc": out["_glm_tc"],
+                     "kernel_ms": {k: v for k, v in pp["ms"].items() if v > 0},
+                     "note": "K9, rank 0: algorithmic IRLS flops (BASELINE.md section 4, at the mean number of solves per cell) over "
+                             "the device time of the projection kernels.  tcgen05 method (proj_tc.cu): all cells in lock step, "
+                             "gradient and Hessian of every Newton sweep from ceil((T+1)/32) launches of fused_tc_kernel's product "
+                             "rider (eta tile and both products on the tensor cores), the last ~2 % of slow cells by the exact fp64 "
+                             "kernel; exact method (proj_irls_kernel): fp64 FMAs on the CUDA cores, fastglm's own iteration"},
         "cpu_baseline": None,
         "e2e": {"value": J / wall, "unit": "cells/s", "seconds": wall, "subsample_fit_device_ms": fit_ms, "projection_ms": proj_ms,
                 "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": float(Jl * (2 * M + 1) * 8),

@@ -232,7 +232,17 @@ typedef struct scgbm_proj_args {
   const int64_t* csc_p;
   const void*    csc_x;
   int32_t  csc_x_dtype;
+  /* how the per-cell GLMs are solved (0 = AUTO):
+   *   SCGBM_GLM_EXACT    one fp64 IRLS per cell exactly as fastglm runs it (start mu = y + 0.1, deviance stop);
+   *   SCGBM_GLM_TCGEN05  all cells in lock step on the tensor cores: Newton from the null model, gradient and
+   *                      Hessian from the fused pass's product rider, stop on the Newton decrement (the predicted
+   *                      deviance change); coefficients agree with the exact path to ~1e-6, `iters` counts Newton
+   *                      solves and may differ from fastglm's; cells that do not converge are finished by the exact
+   *                      kernel.  Needs integer counts (u8 / u16 storage).
+   * AUTO: tcgen05 for integer counts and J >= 4096, else exact. */
+  int32_t  glm_method;
 } scgbm_proj_args;
+enum scgbm_glm_method { SCGBM_GLM_AUTO = 0, SCGBM_GLM_EXACT = 1, SCGBM_GLM_TCGEN05 = 2 };
 
 typedef struct scgbm_proj_out {
   double* beta;       /* J      intercept coefficient (R/fit.R:270)  */
@@ -243,6 +253,9 @@ typedef struct scgbm_proj_out {
   scgbm_profile prof;
   double* rowsum_full; /* I_full or NULL: rowSums(Y) of ALL genes over this call's cells (R/fit.R:217), computed from
                         * the same upload so that the host never has to sweep the I x J matrix itself */
+  int32_t method_used;   /* SCGBM_GLM_EXACT or SCGBM_GLM_TCGEN05                                     */
+  int32_t tc_sweeps;     /* tcgen05: lock-step Newton sweeps run                                      */
+  int64_t tc_stragglers; /* tcgen05: cells handed to the exact kernel                                 */
 } scgbm_proj_out;
 
 int scgbm_project(const scgbm_proj_args* args, scgbm_proj_out* out);

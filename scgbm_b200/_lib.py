@@ -88,12 +88,14 @@ class ProjArgs(C.Structure):
                 ("ixs", C.c_void_p), ("Ik", C.c_int64), ("M", C.c_int32),
                 ("U", C.c_void_p), ("alpha", C.c_void_p), ("glm_tol", C.c_double),
                 ("glm_maxit", C.c_int32), ("device", C.c_int32), ("profile", C.c_int32),
-                ("csc_i", C.c_void_p), ("csc_p", C.c_void_p), ("csc_x", C.c_void_p), ("csc_x_dtype", C.c_int32)]
+                ("csc_i", C.c_void_p), ("csc_p", C.c_void_p), ("csc_x", C.c_void_p), ("csc_x_dtype", C.c_int32),
+                ("glm_method", C.c_int32)]
 
 
 class ProjOut(C.Structure):
     _fields_ = [("beta", C.c_void_p), ("scores", C.c_void_p), ("se_scores", C.c_void_p),
-                ("fail", C.c_void_p), ("iters", C.c_void_p), ("prof", Profile), ("rowsum_full", C.c_void_p)]
+                ("fail", C.c_void_p), ("iters", C.c_void_p), ("prof", Profile), ("rowsum_full", C.c_void_p),
+                ("method_used", C.c_int32), ("tc_sweeps", C.c_int32), ("tc_stragglers", C.c_int64)]
 
 
 class SimArgs(C.Structure):

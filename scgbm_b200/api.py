@@ -103,7 +103,7 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
            batch=None, time_by_iter=False, min_iter=30, *, device=-1, comm=None, y_storage=L.STORE_AUTO,
            svd_extra=0, svd_depth=0, svd_tol=0.0, seed=0, profile=False, verbose=False, quiet=True,
            diagnostics=False, y_device_ptr=None, y_device_shape=None, y_device_dtype=None, rng=None,
-           keep_factors=False, subset_Y=None, ngpu=1, devices=None, batch_levels=None):
+           keep_factors=False, subset_Y=None, ngpu=1, devices=None, batch_levels=None, glm_method="auto"):
     """gbm.sc(Y, M, max.iter, tol, subset, ncores, infer.beta, return.W, batch,
     time.by.iter, min.iter)   -- R/fit.R:52-62.
 
@@ -114,13 +114,14 @@ def gbm_sc(Y, M, max_iter=100, tol=1e-4, subset=None, ncores=1, infer_beta=False
     `_batch`: the factors of the X that alpha/beta/W belong to, so that `get_se` works
     after `return_W=False` -- the reference cannot, quirk Q9), `ngpu` (>= 2: ONE call uses that many GPUs of
     the box -- the library splits the cells over one host thread / NCCL rank per GPU; all outputs cover all
-    cells), `batch_levels` (explicit factor levels; with `comm` they are otherwise agreed across ranks).
+    cells), `batch_levels` (explicit factor levels; with `comm` they are otherwise agreed across ranks),
+    `glm_method` (projection only: "auto" | "exact" | "tcgen05", see gbm_proj_parallel).
     """
     if subset is not None or subset_Y is not None:             # R/fit.R:67-73
         from .projection import gbm_proj_parallel
         out = gbm_proj_parallel(Y, M, subsample=subset if subset is not None else 0, ncores=ncores, tol=tol, max_iter=max_iter,
                                 device=device, rng=rng, profile=profile, svd_tol=svd_tol, seed=seed,
-                                comm=comm, subsample_Y=subset_Y)
+                                comm=comm, subsample_Y=subset_Y, glm_method=glm_method)
         if not quiet:
             print("For users of newer versions (1.0.1+): the `scores` matrix now contains factor scores.",
                   file=sys.stderr)

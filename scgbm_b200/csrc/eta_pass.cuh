@@ -90,8 +90,11 @@ struct FusedProd {
   const float* op_inv;        // device: 1 / operand scale
   int b;                      // block columns, <= 32
   double* out; int64_t ldo;
+  // product only (proj_tc.cu): no residual planes are written -- the launch reads Y, rebuilds W and delivers
+  // (Y - W)^T Q0; `resid` then only carries the scale.  Implies any shard size (no "worth it" threshold).
+  bool product_only = false;
 };
-bool fused_prod_supported(Ctx& ctx, const PassGeom& g, const XDesc& x);
+bool fused_prod_supported(Ctx& ctx, const PassGeom& g, const XDesc& x, bool any_size = false);
 void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const Counts& y, const float* f_row,
                    const float* g_col, const float* la_row, const float* lb_col, const double* alpha,
                    const double* beta, const double* rowsum_local, float maxY, ResidBuf resid, double* out3,

@@ -898,12 +898,12 @@ bool eta_tc_supported(const PassGeom& g, const XDesc& x, int y_storage) {
 
 // the fused first Krylov pass needs: the unclamped low-rank X, enough cell tiles to be worth it, and room
 // for the operand ring beside at least two count stages
-bool fused_prod_supported(Ctx& ctx, const PassGeom& g, const XDesc& x) {
+bool fused_prod_supported(Ctx& ctx, const PassGeom& g, const XDesc& x, bool any_size) {
   const char* knob = getenv("SCGBM_FUSED_PROD");   // "0": off; "force": also below the size threshold (tests)
-  if ((knob && knob[0] == '0') || x.clamp || !x.A16) return false;
+  if ((knob && knob[0] == '0' && !any_size) || x.clamp || !x.A16) return false;
   // one unit per cell tile (see pass_fused_tc): below ~4 tiles per SM the unfilled last wave eats the gain
   const int64_t n_cell_tiles = ceil_div(g.J, FT_CELLS);
-  if (n_cell_tiles < (int64_t)ctx.num_sms * 4 && !(knob && knob[0] == 'f')) return false;
+  if (n_cell_tiles < (int64_t)ctx.num_sms * 4 && !(knob && knob[0] == 'f') && !any_size) return false;
   const int nslab = x.A16->Kp / 64;
   const int fixed = nslab * FT_SLAB_A + FT_NB_PROD * nslab * FT_SLAB_B + 2 * FT_R_BYTES + 1024 + 640 + 4 * FT_GENES * 4 + FT_NOP * FT_OP_BYTES;
   return (232448 - fixed) / (FT_CELLS * FT_GENES * 2) >= 2;
@@ -939,7 +939,8 @@ void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const
   if (getenv("SCGBM_FUSED_CHUNKS")) chunks = std::max(1, atoi(getenv("SCGBM_FUSED_CHUNKS")));   // experiments
   const bool do_prod = prod != nullptr;
   if (do_prod) {
-    SCGBM_REQUIRE(fused_prod_supported(ctx, g, x) && prod->b >= 1 && prod->b <= 32, "fused_tc: product fusion not available for this shape");
+    SCGBM_REQUIRE(fused_prod_supported(ctx, g, x, prod->product_only) && prod->b >= 1 && prod->b <= 32,
+                  "fused_tc: product fusion not available for this shape");
     // One unit owns a cell tile's whole product row: fixed summation order, the very drain cadence of prod_t
     // (bit-identical results), no partial buffers.  Measured alternative -- gene chunks with per-chunk partials
     // summed afterwards -- fills the last wave better but pays the operand/accumulator ramp per unit:
@@ -964,7 +965,7 @@ void pass_fused_tc(Ctx& ctx, EtaWs& ws, const PassGeom& g, const XDesc& x, const
   // back-off in the UMMA issuer; the drain warps poll once per ~3 us pair of tiles
   p.ns_prod = 64; p.ns_mma = 0; p.ns_drain = 400;
   static const bool no_store = getenv("SCGBM_DBG_NO_STORE") != nullptr;
-  p.dbg_no_store = no_store ? 1 : 0;
+  p.dbg_no_store = (no_store || (prod && prod->product_only)) ? 1 : 0;
   const int grid = std::min(p.n_units, ctx.num_sms);
   if (ws.scal_part.n < (int64_t)grid * 4) ws.scal_part.alloc((int64_t)grid * 4);
   p.scal_part = ws.scal_part.get();

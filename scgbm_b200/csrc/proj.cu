@@ -5,6 +5,7 @@
 // X^T W X.  Eight cells share a CTA so each x_a x_b product feeds eight weights.
 #include "wgram.cuh"
 #include "counts.cuh"
+#include "proj_tc.cuh"
 
 namespace scgbm {
 
@@ -19,6 +20,8 @@ struct ProjParams {
   double* se;             // J x p
   int8_t* fail;           // J
   int32_t* iters;         // J
+  int64_t ncell;          // cells this launch fits: J, or the length of `list`
+  const int64_t* list;    // null: cells 0..J-1; else the cells to fit (the tensor-core path's stragglers, proj_tc.cu)
 };
 
 template <typename YT> __device__ __forceinline__ double y_at(const void* Y, int64_t idx) {
@@ -47,7 +50,7 @@ proj_irls_kernel(const ProjParams q) {
   const int64_t c0 = (int64_t)blockIdx.x * WG_CC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // warp = cell slot in the eta phase
   if (threadIdx.x < WG_CC) {
-    state_s[threadIdx.x] = (c0 + threadIdx.x < q.J) ? 0 : 1;
+    state_s[threadIdx.x] = (c0 + threadIdx.x < q.ncell) ? 0 : 1;
     iters_s[threadIdx.x] = 0;
     dev_s[threadIdx.x] = 0.0; devold_s[threadIdx.x] = 0.0;
   }
@@ -65,7 +68,7 @@ proj_irls_kernel(const ProjParams q) {
     for (int c = 0; c < WG_CC; ++c) racc[c] = 0.0;
     double dev_part = 0.0;     // this thread's (gene lane, cell = warp) share of the deviance
     const bool cell_live = state_s[warp] == 0;
-    const int64_t cell = c0 + warp;
+    const int64_t cell = (c0 + warp < q.ncell) ? (q.list ? q.list[c0 + warp] : c0 + warp) : 0;
 
     for (int64_t r0 = 0; r0 < q.Ik; r0 += WG_TR) {
       __syncthreads();
@@ -155,15 +158,16 @@ proj_irls_kernel(const ProjParams q) {
   // outputs
   for (int idx = threadIdx.x; idx < WG_CC * p; idx += WG_NT) {
     const int c = idx / p, a = idx % p;
-    const int64_t cellj = c0 + c;
-    if (cellj >= q.J) continue;
+    if (c0 + c >= q.ncell) continue;
+    const int64_t cellj = q.list ? q.list[c0 + c] : c0 + c;
     const bool bad = state_s[c] == 2;
     q.coef[(int64_t)a * q.J + cellj] = bad ? 0.0 : b_s[c * p + a];
     q.se[(int64_t)a * q.J + cellj] = bad ? 0.0 : sqrt(se_s[c * p + a]);
   }
-  if (threadIdx.x < WG_CC && c0 + threadIdx.x < q.J) {
-    q.fail[c0 + threadIdx.x] = state_s[threadIdx.x] == 2 ? 1 : 0;
-    if (q.iters) q.iters[c0 + threadIdx.x] = iters_s[threadIdx.x];
+  if (threadIdx.x < WG_CC && c0 + threadIdx.x < q.ncell) {
+    const int64_t cellj = q.list ? q.list[c0 + threadIdx.x] : c0 + threadIdx.x;
+    q.fail[cellj] = state_s[threadIdx.x] == 2 ? 1 : 0;
+    if (q.iters) q.iters[cellj] = iters_s[threadIdx.x];
   }
 }
 
@@ -230,12 +234,28 @@ void project_impl(const scgbm_proj_args* a, scgbm_proj_out* out) {
   q.tol = a->glm_tol > 0 ? a->glm_tol : 1e-8;
   q.maxit = a->glm_maxit > 0 ? a->glm_maxit : 100;
   q.coef = coef.get(); q.se = se.get(); q.fail = fail.get(); q.iters = iters.get();
+  q.ncell = J; q.list = nullptr;
   const size_t smem = (size_t)(WG_TR * (p + 1) + 2 * WG_TR * WG_CC + 3 * WG_CC * p + (size_t)WG_CC * p * p + 2 * WG_CC) * sizeof(double) +
                       2 * WG_CC * sizeof(int) + 2 * (size_t)T * sizeof(unsigned short) + 32;
   SCGBM_REQUIRE(smem <= 220 * 1024, "projection: M too large for shared memory");
-  {
+  // Method (scgbm_proj_args.glm_method; SCGBM_PROJ_METHOD overrides for experiments): the tensor-core path runs all
+  // cells in lock step through the fused pass's product rider (proj_tc.cu) and leaves only its stragglers to the
+  // exact kernel; AUTO takes it for integer counts once there are enough cells to fill the machine.
+  int method = a->glm_method;
+  if (const char* e = getenv("SCGBM_PROJ_METHOD")) method = atoi(e);
+  SCGBM_REQUIRE(method >= SCGBM_GLM_AUTO && method <= SCGBM_GLM_TCGEN05, "glm_method must be 0 (auto), 1 (exact) or 2 (tcgen05)");
+  const bool tc_ok = proj_tc_supported(ctx, Y, M);
+  SCGBM_REQUIRE(method != SCGBM_GLM_TCGEN05 || tc_ok, "glm_method = tcgen05 needs integer counts (u8 / u16 storage) and M <= 64");
+  const bool use_tc = method == SCGBM_GLM_TCGEN05 || (method == SCGBM_GLM_AUTO && tc_ok && J >= 4096);
+  DevBuf<int64_t> list;
+  ProjTcStats tcs;
+  if (use_tc) {
+    q.ncell = project_tc(ctx, Y, Ik, M, U.get(), off.get(), q.tol, 30, coef.get(), se.get(), fail.get(), iters.get(), list, &tcs);
+    q.list = list.get();
+  }
+  if (q.ncell > 0) {
     ProfScope ps(ctx.prof, SCGBM_K_PROJ, 1);
-    const unsigned grid = (unsigned)ceil_div(J, WG_CC);
+    const unsigned grid = (unsigned)ceil_div(q.ncell, WG_CC);
     switch (PT) {
       case 1: launch_proj<1>(ctx, q, Y.storage, grid, smem); break;
       case 2: launch_proj<2>(ctx, q, Y.storage, grid, smem); break;
@@ -244,6 +264,9 @@ void project_impl(const scgbm_proj_args* a, scgbm_proj_out* out) {
       default: launch_proj<9>(ctx, q, Y.storage, grid, smem); break;
     }
   }
+  out->method_used = use_tc ? SCGBM_GLM_TCGEN05 : SCGBM_GLM_EXACT;
+  out->tc_sweeps = tcs.sweeps;
+  out->tc_stragglers = use_tc ? q.ncell : 0;
   // V[, 1] = beta, V[, 2:(M+1)] = scores, se[-1] = se_scores   (R/fit.R:258-270)
   SCGBM_CUDA(cudaMemcpyAsync(out->beta, coef.get(), J * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
   SCGBM_CUDA(cudaMemcpyAsync(out->scores, coef.get() + J, J * M * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));

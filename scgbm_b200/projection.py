@@ -13,12 +13,15 @@ from . import _lib as L
 
 def gbm_proj_parallel(Y, M, subsample=2000, min_counts=5, ncores=1, tol=1e-4, max_iter=100, *,
                       device=-1, rng=None, profile=False, svd_tol=0.0, seed=0, glm_tol=1e-8, glm_maxit=100,
-                      comm=None, subsample_Y=None):
+                      glm_method="auto", comm=None, subsample_Y=None):
     """Cells sharded over ranks (BASELINE configs[3]): pass `comm` and the
     subsample's count matrix `subsample_Y` (I x s, the same on every rank -- the host
     harness gathers those columns).  Y then holds this rank's cells only; every rank
     runs the identical subsample fit (bit-reproducible), projects its own cells, and the
-    only exchanges are the gene row sums and the scalar sum(exp(beta)) of R/fit.R:274."""
+    only exchanges are the gene row sums and the scalar sum(exp(beta)) of R/fit.R:274.
+
+    glm_method: "exact" (one fp64 IRLS per cell, fastglm's iteration), "tcgen05" (all cells in lock step on the tensor
+    cores, include/scgbm.h scgbm_glm_method) or "auto" (tcgen05 for integer counts and >= 4096 cells)."""
     from .api import gbm_sc, _as_counts, _is_sparse, _NP2DT, _canonical_csc
     lib = L.load()
     if (comm is None) != (subsample_Y is None):
@@ -67,6 +70,7 @@ def gbm_proj_parallel(Y, M, subsample=2000, min_counts=5, ncores=1, tol=1e-4, ma
         a.Y = L.ptr(Yh); a.y_dtype = y_dt; a.y_on_device = 0; a.I_full = I; a.J = J; a.ldY = I
     a.ixs = L.ptr(ixs64); a.Ik = len(ixs64); a.M = int(M); a.U = L.ptr(Uk); a.alpha = L.ptr(alpha_k)
     a.glm_tol = float(glm_tol); a.glm_maxit = int(glm_maxit); a.device = int(device); a.profile = int(bool(profile))
+    a.glm_method = {"auto": 0, "exact": 1, "tcgen05": 2}[glm_method]
     o = L.ProjOut()
     o.beta = L.ptr(beta); o.scores = L.ptr(scores); o.se_scores = L.ptr(se_scores)
     o.fail = L.ptr(fail); o.iters = L.ptr(iters)
@@ -97,6 +101,8 @@ def gbm_proj_parallel(Y, M, subsample=2000, min_counts=5, ncores=1, tol=1e-4, ma
     out["V"] = None                                                        # :281
     out["loadings"] = None   # :282 assigns the undefined `loadings` (stats::loadings): a reference bug
     out["_ixs"] = ixs; out["_jxs"] = jxs; out["_fail"] = fail.astype(bool); out["_glm_iters"] = iters
+    out["_glm_method"] = {2: "tcgen05"}.get(o.method_used, "exact")
+    out["_glm_tc"] = dict(sweeps=o.tc_sweeps, stragglers=o.tc_stragglers)
     if profile:
         out["_prof_proj"] = o.prof.as_dict()
     return out

@@ -374,3 +374,81 @@ def test_packed_epilogue_agrees_with_the_plain_form(rider, monkeypatch):
     np.testing.assert_allclose(packed["_LL"], plain["_LL"], rtol=1e-8)
     np.testing.assert_allclose(packed["alpha"], plain["alpha"], atol=1e-7)
     assert principal_angle(packed["U"], plain["U"]) < 1e-6
+
+
+def _glm_problem(Ik, J, M, seed, scale=3.0):
+    rng = np.random.default_rng(seed)
+    U, _ = np.linalg.qr(rng.standard_normal((Ik, M)))
+    alpha = rng.normal(0, 0.7, Ik)
+    sc = rng.normal(0, scale, (J, M)); b0 = rng.normal(0.2, 0.5, J)
+    Y = rng.poisson(np.exp(alpha[:, None] + b0[None, :] + U @ sc.T)).astype(np.int32)
+    return U, alpha, Y
+
+
+def _project(U, alpha, Y, method, tol=1e-8):
+    import ctypes as C
+    from scgbm_b200 import _lib as L
+    Ik, J = Y.shape; M = U.shape[1]
+    Yf = np.asfortranarray(Y); Uf = np.asfortranarray(U); ixs = np.arange(Ik, dtype=np.int64)
+    beta = np.zeros(J); scores = np.zeros((J, M), order="F"); se = np.zeros((J, M), order="F")
+    fail = np.zeros(J, dtype=np.int8); iters = np.zeros(J, dtype=np.int32)
+    a = L.ProjArgs()
+    a.Y = L.ptr(Yf); a.y_dtype = L.I32; a.I_full = Ik; a.J = J; a.ldY = Ik; a.ixs = L.ptr(ixs); a.Ik = Ik; a.M = M
+    a.U = L.ptr(Uf); a.alpha = L.ptr(alpha); a.glm_tol = tol; a.glm_maxit = 100; a.device = -1; a.glm_method = method
+    o = L.ProjOut(); o.beta = L.ptr(beta); o.scores = L.ptr(scores); o.se_scores = L.ptr(se)
+    o.fail = L.ptr(fail); o.iters = L.ptr(iters)
+    L.check(L.load().scgbm_project(C.byref(a), C.byref(o)))
+    return dict(beta=beta, scores=scores, se=se, fail=fail, iters=iters, method=o.method_used, sweeps=o.tc_sweeps,
+                stragglers=o.tc_stragglers)
+
+
+@pytest.mark.parametrize("Ik,J,M,seed", [(700, 300, 6, 5), (1100, 520, 20, 6), (260, 200, 3, 7)])
+def test_projection_tcgen05_matches_fastglm_restatement(Ik, J, M, seed):
+    """K9 on the tensor cores (proj_tc.cu: lock-step Newton, gradient and Hessian from the fused pass's product rider)
+    against the fastglm restatement, cell by cell.  Tolerances of this path (include/scgbm.h, scgbm_glm_method):
+    coefficients 2e-6 (eta carries 22 bits, exp is ex2.approx), standard errors 1e-3 relative (fastglm reports the
+    X^T W X of its LAST SOLVE, i.e. one step before the returned coefficients, so that number depends on the path
+    by the size of the last step); the exact kernel holds 1e-9 for both (test_projection_glm_kernel_exact).
+    A cell without counts, and the last percent of slow cells, take the exact kernel."""
+    from oracle.scgbm_oracle import poisson_glm_irls
+    U, alpha, Y = _glm_problem(Ik, J, M, seed)
+    Y[:, 17] = 0                                            # no counts: handed to the exact kernel
+    tc = _project(U, alpha, Y, 2)
+    ex = _project(U, alpha, Y, 1)
+    assert tc["method"] == 2 and ex["method"] == 1
+    assert 1 <= tc["stragglers"] <= J // 20 + 2, tc              # the empty cell, and at most a few slow ones
+    assert 3 <= tc["sweeps"] <= 30
+    np.testing.assert_array_equal(tc["fail"], ex["fail"])
+    ok = ex["fail"] == 0
+    # against the exact kernel (itself pinned to the oracle at 1e-9) for every cell ...
+    np.testing.assert_allclose(tc["beta"][ok], ex["beta"][ok], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(tc["scores"][ok], ex["scores"][ok], rtol=2e-6, atol=2e-6 * np.abs(ex["scores"][ok]).max())
+    np.testing.assert_allclose(tc["se"][ok], ex["se"][ok], rtol=1e-3)
+    # ... and against the oracle directly for a sample of them
+    Xd = np.hstack([np.ones((Ik, 1)), U])
+    for j in range(0, J, max(1, J // 12)):
+        if not ok[j]:
+            continue
+        coef, sej, conv, nit = poisson_glm_irls(Xd, Y[:, j].astype(float), alpha)
+        np.testing.assert_allclose(tc["beta"][j], coef[0], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(tc["scores"][j], coef[1:], rtol=2e-6, atol=2e-6 * np.abs(coef[1:]).max())
+        np.testing.assert_allclose(tc["se"][j], sej[1:], rtol=1e-3)
+        assert 1 <= int(tc["iters"][j]) <= nit + 2          # Newton solves from the null model vs fastglm's IRLS count
+
+
+def test_projection_tcgen05_through_gbm_sc_subset():
+    """gbm.sc(subset = idx) with the tensor-core projection against the exact one: same subsample fit, scores / beta /
+    alpha within the path's tolerance; AUTO keeps the exact kernel below 4096 cells."""
+    from scgbm_b200 import gbm_sc
+    Y = _sim(260, 900, 4, seed=31, bmean=0.5)
+    idx = np.arange(1, 301)
+    ex = gbm_sc(Y, 4, subset=idx, glm_method="exact")
+    tc = gbm_sc(Y, 4, subset=idx, glm_method="tcgen05")
+    auto = gbm_sc(Y, 4, subset=idx)
+    assert ex["_glm_method"] == "exact" and tc["_glm_method"] == "tcgen05" and auto["_glm_method"] == "exact"
+    assert not tc["_fail"].any()
+    np.testing.assert_allclose(tc["scores"], ex["scores"], rtol=2e-6, atol=2e-6 * np.abs(ex["scores"]).max())
+    np.testing.assert_allclose(tc["se_scores"], ex["se_scores"], rtol=1e-3)
+    np.testing.assert_allclose(tc["beta"], ex["beta"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(tc["alpha"], ex["alpha"], rtol=0, atol=2e-6)
+    np.testing.assert_array_equal(tc["U"], ex["U"])
