@@ -14,11 +14,11 @@ J = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 I = 20000
 lib = L.load()
-wl = bench.Workload(I, J, M)
+cfg = dict(bench.CONFIGS["c5p"], I=I, J=J, M=M, d=M)
 ldI = (I + 63) // 64 * 64
 ydev = C.c_void_p()
 L.check(lib.scgbm_dev_alloc(C.byref(ydev), ldI * J * 2, 0))
-wl.sim_into(lib, L, ydev, 0, J, ldI, L.U16, 0)
+bench.sim_into_device(lib, L, cfg, ydev, 0, J, ldI, L.U16, 0)
 a = L.FitArgs()
 a.Y = ydev; a.y_dtype = L.U16; a.y_on_device = 1; a.I = I; a.J = J; a.ldY = ldI
 a.M = M; a.max_iter = 5; a.tol = 1e-4; a.min_iter = 10 ** 6; a.nbatch = 1; a.y_storage = L.STORE_U16; a.device = 0
