@@ -105,7 +105,7 @@ typedef struct scgbm_fit_args {
   scgbm_comm* comm;     /* NULL: single GPU; else cells are sharded over the ranks  */
   int32_t  svd_extra;   /* Krylov block = M + svd_extra   (default 12)              */
   int32_t  svd_depth;   /* max Krylov extensions per cycle (default 3)              */
-  double   svd_tol;     /* Ritz residual estimate to stop at (default 1e-4)         */
+  double   svd_tol;     /* Ritz residual estimate to stop at (0: 1e-5, irlba's default) */
   uint64_t seed;        /* start block of the initial SVD                           */
   int32_t  profile;     /* 1: per-class CUDA-event timing into out->prof; 2: only the */
                         /* fused pass (K4) is bracketed by events (launch counts stay) */

@@ -234,6 +234,7 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
   int maxM = 1;
   for (int t = 0; t < op.nterms; ++t) maxM = std::max(maxM, op.t[t].M);
   const bool was_warm = ws.warm && ws.b == b;
+  const double tol = (was_warm && o.tol_warm > 0.0) ? o.tol_warm : o.tol;
   tsvd_alloc(ws, ldI, ldJ, b, b * ((was_warm ? depth_warm : depth_cold) + 1), maxM);
   const int pmax = ws.pmax;
   int depth = std::min(was_warm ? depth_warm : depth_cold, pmax / b - 1);
@@ -241,7 +242,7 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
   // below tol^2.  Measured: objective trace 2e-6, angles 1e-4 -- outside the parity tolerances.
   static const int env_fast = getenv("SCGBM_SVD_FAST") ? atoi(getenv("SCGBM_SVD_FAST")) : -1;
   const bool allow_fast = env_fast >= 0 ? env_fast != 0 : o.fast != 0;
-  const bool fast_call = allow_fast && was_warm && depth > 0 && ws.last_est < o.tol * o.tol && ws.fast_streak < 3;
+  const bool fast_call = allow_fast && was_warm && depth > 0 && ws.last_est < tol * tol && ws.fast_streak < 3;
   if (fast_call) depth = 0;
 
   int passes = 0;
@@ -332,7 +333,7 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
           est = h[0];
           if (!(h[1] == h[1])) throw Error(SCGBM_ERR_NUMERIC, "truncated SVD: non-finite Ritz values");
           if (h[2] != 0.0 && !robust) { restart = true; break; }   // a Cholesky pivot vanished: redo robustly
-          if (t > 0 && est < o.tol) break;
+          if (t > 0 && est < tol) break;
         }
         if (last) break;
         op_mul(ctx, ws, op, Zt, ldJ, b, ws.Qb.get() + (int64_t)(t + 1) * b * ldI, o.variant);
@@ -351,9 +352,9 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
       ts_mul(ctx, op.J, p, b, ws.Zb.get(), ldJ, ws.C.get(), p, ws.Vwarm.get(), ldJ, 1.0, 0.0);
       static const bool trace = getenv("SCGBM_TRACE") != nullptr;
       if (trace) fprintf(stderr, "[scgbm-trace]   tsvd %s cycle %d: p=%d passes so far %d est %.3e\n", was_warm ? "warm" : "cold", cycle, p, passes, est);
-      bool converged = est < o.tol || depth == 0;
+      bool converged = est < tol || depth == 0;
       if (ws.lowprec) {
-        if (est < 30.0 * o.tol || cycle + 5 >= o.max_cycles) ws.lowprec = false;
+        if (est < 30.0 * tol || cycle + 5 >= o.max_cycles) ws.lowprec = false;
         converged = false;
       }
       if (converged || cycle + 1 >= o.max_cycles || (was_warm && cycle >= 1)) break;
@@ -370,7 +371,7 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
   else { ws.fast_streak = 0; ws.last_est = est; }
   // irlba would iterate on (to maxit) and warn; here the cycle budget is fixed, so an estimate that is still
   // above the tolerance is reported (scgbm_fit_out.svd_unconverged / svd_worst_est; the wrappers warn)
-  if (!fast_call && !(est < o.tol)) { ++ws.unconverged; ws.worst_est = std::max(ws.worst_est, est); }
+  if (!fast_call && !(est < tol)) { ++ws.unconverged; ws.worst_est = std::max(ws.worst_est, est); }
   copy_mat(ctx, ldI, M, ws.Ub.get(), ldI, outU, ldI);
   copy_mat(ctx, op.J, M, ws.Vwarm.get(), ldJ, outV, ldJ);
   SCGBM_CUDA(cudaMemcpyAsync(outD, ws.Tw.get(), M * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));

@@ -35,7 +35,8 @@ struct TsvdOpts {
   int extra = 12;       // block = M + extra
   int depth = 3;        // Krylov extensions per cycle (warm start)
   int cold_depth = 7;   // ... on a cold start (fewer, deeper cycles; the p = 8b Ritz problem runs on the cooperative Jacobi)
-  double tol = 1e-4;    // Ritz residual estimate
+  double tol = 1e-4;    // Ritz residual estimate (cold start)
+  double tol_warm = 0;  // ... of the warm calls inside the loop (0: = tol)
   int max_cycles = 40;  // restarts (cold start on gap-less spectra)
   uint64_t seed = 0;
   int variant = PROD_AUTO;
