@@ -117,11 +117,23 @@ Ctx::~Ctx() {
   if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
 }
 
+// Sum over ranks, with the SAME BITS on every rank afterwards.  Everything gene-sided (Krylov bases, Gram matrices,
+// alpha, the objective) is replicated: each rank recomputes it from its own copy of the all-reduced partial products.
+// A sum all-reduce only promises every rank A correctly rounded sum of the contributions; from four ranks on the
+// association order -- hence the last bit -- may differ from rank to rank (two ranks cannot differ: a + b = b + a).
+// A max all-reduce has no such freedom (max is exactly associative), so the sum is followed by one: every rank ends
+// up with the largest of the candidates, bit for bit.  Cost: one more latency-bound collective per site (messages
+// are <= 5 MB).  (Identical inputs turned out to be necessary but not sufficient for identical replicated state:
+// see svd_bcast in tsvd.cu.)
 void Ctx::allreduce_sum(double* dev, int64_t n) {
   if (!comm || nranks == 1 || n <= 0) return;
   if (comm->group) inproc_arrive(comm);
-  ProfScope ps(prof, SCGBM_K_COMM, 1);
+  ProfScope ps(prof, SCGBM_K_COMM, nranks > 2 ? 2 : 1);
   SCGBM_NCCL(nccl().AllReduce(dev, dev, (size_t)n, ncclFloat64, ncclSum, comm->comm, stream));
+  if (nranks > 2) {
+    if (comm->group) { SCGBM_CUDA(cudaStreamSynchronize(stream)); inproc_arrive(comm); }
+    SCGBM_NCCL(nccl().AllReduce(dev, dev, (size_t)n, ncclFloat64, ncclMax, comm->comm, stream));
+  }
   if (comm->group) SCGBM_CUDA(cudaStreamSynchronize(stream));
 }
 void Ctx::allreduce_max(double* dev, int64_t n) {
@@ -130,6 +142,43 @@ void Ctx::allreduce_max(double* dev, int64_t n) {
   ProfScope ps(prof, SCGBM_K_COMM, 1);
   SCGBM_NCCL(nccl().AllReduce(dev, dev, (size_t)n, ncclFloat64, ncclMax, comm->comm, stream));
   if (comm->group) SCGBM_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Ctx::bcast0(double* dev, int64_t n) {
+  if (!comm || nranks == 1 || n <= 0) return;
+  if (rank != 0) SCGBM_CUDA(cudaMemsetAsync(dev, 0, (size_t)n * sizeof(double), stream));
+  allreduce_sum(dev, n);        // x + 0 + ... + 0 is exact in any order
+}
+
+__global__ void __launch_bounds__(1024) checksum_kernel(int64_t n, const double* __restrict__ x, double* __restrict__ out) {
+  __shared__ double red[1024];
+  double s = 0.0, a = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) { s += x[i] * (double)(1 + (i % 7)); a += fabs(x[i]); }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int st = 512; st > 0; st >>= 1) { if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st]; __syncthreads(); }
+  const double cs = red[0];
+  __syncthreads();
+  red[threadIdx.x] = a;
+  __syncthreads();
+  for (int st = 512; st > 0; st >>= 1) { if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st]; __syncthreads(); }
+  if (threadIdx.x == 0) { out[0] = cs; out[1] = -cs; out[2] = red[0]; }
+}
+
+void Ctx::rank_spread(const char* what, int call, const double* dev, int64_t n) {
+  static const bool on = getenv("SCGBM_RANKCHECK") != nullptr;
+  if (!on || !comm || nranks == 1 || n <= 0) return;
+  double* d = nullptr;
+  SCGBM_CUDA(cudaMalloc((void**)&d, 4 * sizeof(double)));
+  checksum_kernel<<<1, 1024, 0, stream>>>(n, dev, d);
+  allreduce_max(d, 3);
+  double h[3];
+  SCGBM_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  sync();
+  cudaFree(d);
+  const double spread = h[0] + h[1];
+  if (rank == 0 && spread != 0.0)
+    fprintf(stderr, "[scgbm-rankcheck] call %d %s: checksum spread %.3e (sum |x| %.3e, n %lld)\n", call, what, spread, h[2], (long long)n);
 }
 
 Comm* comm_create(const uint8_t* id, int nranks, int rank, int device) {

@@ -180,6 +180,11 @@ struct Ctx {
   // collectives on device buffers (no-ops when single rank)
   void allreduce_sum(double* dev, int64_t n);
   void allreduce_max(double* dev, int64_t n);
+  // every rank ends up with rank 0's copy of a replicated quantity, bit for bit (no-op on a single rank)
+  void bcast0(double* dev, int64_t n);
+  // diagnostics (SCGBM_RANKCHECK): how far the ranks' copies of a replicated quantity are apart
+  // (weighted checksum, max - min over ranks; 0 when they are identical); prints on rank 0
+  void rank_spread(const char* what, int call, const double* dev, int64_t n);
 };
 
 #define SCGBM_LAUNCH_CHECK() SCGBM_CUDA(cudaGetLastError())

@@ -468,7 +468,7 @@ struct FitState {
     // products and do not notice, but the late iterations of a converging fit do -- the complete 100-iteration fit at
     // 20k x 1M took 11.9 s instead of 11.1 s (3e-6: 11.9 s as well), for final objectives 3e-10 apart.  What it would
     // buy: the objective of a REJECTED overshoot step right after a revert, a value the reference never returns,
-    // moved from 6e-6 to within 1e-6 of the exact-SVD oracle on 4 and 8 ranks (tests/test_gpu_multi.py holds
+    // moved from 6e-6 to within 1e-6 of the exact-SVD float64 reference fit on 4 and 8 ranks (tests/test_gpu_multi.py holds
     // rejected iterations to 1e-5 and accepted ones to 1e-6).
     static const double env_tolw = getenv("SCGBM_SVD_TOL_WARM") ? atof(getenv("SCGBM_SVD_TOL_WARM")) : 0.0;   // experiments
     o.tol_warm = env_tolw > 0 ? env_tolw : o.tol;
@@ -567,6 +567,7 @@ struct FitRun {
       beta_shift_kernel<<<GRID1(J)>>>(J, st.beta.get(), st.shift.get());          // R/fit.R:131-132
       SCGBM_LAUNCH_CHECK();
     }
+    ctx.rank_spread("alpha", i, st.alpha.get(), ldI * nbatch);
     st.stage_rows();
     if (a.infer_beta) {                                  // R/fit.R:133-135
       if (tc_eta && nbatch == 1) pass_colsum_tc(ctx, st.eta, st.geom, xc, st.f_row.get(), st.Ccol.get());
@@ -612,7 +613,11 @@ struct FitRun {
       fused_bytes = fused_pass_bytes(st.geom, xm, st.Y.elem_bytes());
     }
     ctx.allreduce_sum(st.scal.get(), 2);
-    ctx.allreduce_max(st.scal.get() + 2, 2);             // max W and the underflow flag of the tensor-core pass
+    // max W and the underflow flag of the tensor-core pass -- and the two sums once more: every accept / revert /
+    // stop decision below is taken by each rank on its own copy of these scalars, so the copies must be IDENTICAL.
+    // A sum all-reduce need not return the same last bit on every rank (the association order may differ between
+    // ranks from 4 ranks on; with 2 it cannot, a + b = b + a); a max all-reduce does, whatever the order.
+    ctx.allreduce_max(st.scal.get(), 4);
     double h[4];
     SCGBM_CUDA(cudaMemcpyAsync(h, st.scal.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
     ctx.sync();

@@ -143,6 +143,21 @@ __global__ void maxdiff_kernel(int64_t n, const double* __restrict__ a, const do
   }
 }
 
+// Rank 0 is the authority for the replicated state of the SVD (several ranks only; SCGBM_SVD_BCAST=0 disables it for
+// experiments).  Every rank recomputes the gene-side quantities -- Krylov blocks, Ritz vectors, the left Ritz block
+// that starts the next call -- from its own copy of the all-reduced products, on the assumption that identical inputs
+// give identical outputs.  Measured on 4 ranks (scripts/gpu_rank_consistency.py, SCGBM_RANKCHECK=1): with bit-identical
+// Gram matrices the eigensolver's output still differed between GPUs in the 14th digit from the very first call, and
+// the left start carries such a difference forward undamped (U_new = Q0 S0 + Q1 S1 with S0 ~ I once converged) while
+// the near-degenerate noise directions of the block amplify it: after 35 iterations the ranks' U were 4e-4 apart and
+// the returned U 2.8e-3 rad off the float64 reference fit's (V, one multiplication by G^T further on, stayed at 8e-6).  With rank
+// 0's S, theta, orthonormalised blocks and Ritz block imposed on every rank the 4-rank fit is as close to that reference
+// as the one-GPU fit: U 3.1e-6, V 3.0e-6, every objective (rejected steps included) within 2e-7.
+static bool svd_bcast(const Ctx& ctx) {
+  static const char* env = getenv("SCGBM_SVD_BCAST");
+  return env ? env[0] != '0' : ctx.nranks > 1;
+}
+
 static bool ustart_enabled() {
   static const bool on = getenv("SCGBM_USTART") ? atoi(getenv("SCGBM_USTART")) != 0 : true;
   return on;
@@ -249,7 +264,8 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
   double est = 1e300;
   // a cold start runs many restarted cycles whose late Krylov blocks are nearly dependent on the
   // converged directions: orthonormalise through the eigen-decomposition from the start there
-  bool robust = ws.robust || !was_warm;
+  static const bool env_robust = getenv("SCGBM_SVD_ROBUST") != nullptr;   // experiments: eigen-based orthonormalisation throughout
+  bool robust = ws.robust || !was_warm || env_robust;
   for (int attempt = 0; attempt < 2; ++attempt) {
     bool restart = false;
     ws.flag.zero(ctx.stream);
@@ -292,6 +308,7 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
         op_mul(ctx, ws, op, V0, ldJ, b, ws.Qb.get(), o.variant, true);
         ++passes;
         sym_orth(ctx, ws.small, ldI, b, ws.Qb.get(), ldI, nullptr, ldI, 0, ws.tmpI.get(), robust, ws.flag.get());
+        if (svd_bcast(ctx)) ctx.bcast0(ws.Qb.get(), ldI * (int64_t)b);
       }
       for (int t = 0;; ++t) {
         p = b * (t + 1);
@@ -320,13 +337,20 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
             copy_lead_kernel<<<(unsigned)ceil_div(p * p, 256), 256, 0, ctx.stream>>>(p, ws.T.get(), pmax, ws.Tw.get());
             SCGBM_LAUNCH_CHECK();
           }
+          ctx.rank_spread("T (Gram, before the Ritz eigensolve)", ws.calls, ws.T.get(), (int64_t)pmax * pmax);
           eigh_desc(ctx, ws.small, p, ws.Tw.get(), ws.theta.get(), ws.S.get());
+          ctx.rank_spread("S (Ritz vectors)", ws.calls, ws.S.get(), (int64_t)p * p);
+          ctx.rank_spread("theta", ws.calls, ws.theta.get(), p);
+          if (svd_bcast(ctx)) { ctx.bcast0(ws.S.get(), (int64_t)p * p); ctx.bcast0(ws.theta.get(), p); }
           {
             ProfScope ps(ctx.prof, SCGBM_K_SMALL, 1);
             ritz_est_kernel<<<1, 64, 0, ctx.stream>>>(p, b, t * b, M, ws.S.get(), ws.theta.get(), ws.T.get(), pmax,
                                                       ws.est.get(), ws.flag.get());
             SCGBM_LAUNCH_CHECK();
           }
+          // the ranks derive the estimate from their own copy of the all-reduced Gram matrix; agree on ONE value
+          // before it decides how many more products (collectives!) this call issues (see FitRun::step)
+          ctx.allreduce_max(ws.est.get(), 3);
           double h[3];
           SCGBM_CUDA(cudaMemcpyAsync(h, ws.est.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
           ctx.sync();
@@ -338,8 +362,11 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
         if (last) break;
         op_mul(ctx, ws, op, Zt, ldJ, b, ws.Qb.get() + (int64_t)(t + 1) * b * ldI, o.variant);
         ++passes;
+        ctx.rank_spread("G Z (all-reduced product, before orthonormalisation)", ws.calls, ws.Qb.get() + (int64_t)(t + 1) * b * ldI, ldI * (int64_t)b);
         sym_orth(ctx, ws.small, ldI, b, ws.Qb.get() + (int64_t)(t + 1) * b * ldI, ldI, ws.Qb.get(), ldI, p,
                  ws.tmpI.get(), robust, ws.flag.get());
+        ctx.rank_spread("Q_t+1 (after orthonormalisation)", ws.calls, ws.Qb.get() + (int64_t)(t + 1) * b * ldI, ldI * (int64_t)b);
+        if (svd_bcast(ctx)) ctx.bcast0(ws.Qb.get() + (int64_t)(t + 1) * b * ldI, ldI * (int64_t)b);
       }
       if (restart) break;
       // Ritz vectors of the leading b pairs
@@ -348,7 +375,10 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
         ritz_scale_kernel<<<(unsigned)ceil_div(p * b, 256), 256, 0, ctx.stream>>>(p, b, ws.S.get(), ws.theta.get(), ws.C.get(), ws.Tw.get());
         SCGBM_LAUNCH_CHECK();
       }
+      ctx.rank_spread("Qb (Krylov basis)", ws.calls, ws.Qb.get(), ldI * (int64_t)p);
       ts_mul(ctx, ldI, p, b, ws.Qb.get(), ldI, ws.S.get(), p, ws.Ub.get(), ldI, 1.0, 0.0);
+      ctx.rank_spread("Ub (left Ritz block)", ws.calls, ws.Ub.get(), ldI * (int64_t)b);
+      if (svd_bcast(ctx)) ctx.bcast0(ws.Ub.get(), ldI * (int64_t)b);
       ts_mul(ctx, op.J, p, b, ws.Zb.get(), ldJ, ws.C.get(), p, ws.Vwarm.get(), ldJ, 1.0, 0.0);
       static const bool trace = getenv("SCGBM_TRACE") != nullptr;
       if (trace) fprintf(stderr, "[scgbm-trace]   tsvd %s cycle %d: p=%d passes so far %d est %.3e\n", was_warm ? "warm" : "cold", cycle, p, passes, est);
@@ -357,7 +387,10 @@ void tsvd(Ctx& ctx, TsvdWs& ws, const GOperator& op, const TsvdOpts& o, double* 
         if (est < 30.0 * tol || cycle + 5 >= o.max_cycles) ws.lowprec = false;
         converged = false;
       }
-      if (converged || cycle + 1 >= o.max_cycles || (was_warm && cycle >= 1)) break;
+      // A warm call used to stop after its second cycle whatever the estimate (round 1), returning factors that could
+      // be 2e-3 rad off when the warm start was poor (right after reverts, late in a fit) -- irlba iterates on.
+      // It now restarts like a cold call, within its own budget; the unconverged counter reports what is left.
+      if (converged || cycle + 1 >= (was_warm ? std::min(o.max_cycles, o.max_warm_cycles) : o.max_cycles)) break;
       V0 = ws.Vwarm.get();
     }
     if (!restart) break;

@@ -38,6 +38,7 @@ struct TsvdOpts {
   double tol = 1e-4;    // Ritz residual estimate (cold start)
   double tol_warm = 0;  // ... of the warm calls inside the loop (0: = tol)
   int max_cycles = 40;  // restarts (cold start on gap-less spectra)
+  int max_warm_cycles = 8;  // ... of a warm call that is still above the tolerance after its first cycle
   uint64_t seed = 0;
   int variant = PROD_AUTO;
   int fast = 0;         // allow 2-pass calls (no Krylov extension) while the previous estimate is < tol^2

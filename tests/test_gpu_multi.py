@@ -63,7 +63,8 @@ def _worker(rank, world, port, q, kw):
         j0, j1 = shard_range(Y.shape[1], rank, world)
         out = gbm_sc(np.asfortranarray(Y[:, j0:j1]), 8, device=rank, comm=comm, diagnostics=True, return_W=False, **kw)
         comm.destroy()
-        q.put((rank, j0, j1, out["_LL"], out["_accepted"], out["alpha"], out["beta"], out["U"], out["V"], out["D"]))
+        q.put((rank, j0, j1, out["_LL"], out["_accepted"], out["alpha"], out["beta"], out["U"], out["V"], out["D"],
+               out["_svd_unconverged"], out["_svd_worst_est"], out["_prof"]["svd_passes"]))
     finally:
         dist.destroy_process_group()
 
@@ -84,8 +85,8 @@ def _check_trace(LL, accepted, one, ref, what):
     reference may differ from one another by twice that bound."""
     from tests.util import first_knife_edge, TOL_OBJ_REL
     k = min(first_knife_edge(ref), len(LL), len(one["_LL"]))
-    np.testing.assert_array_equal(accepted[:k], ref["_accepted"][:k])
-    np.testing.assert_array_equal(accepted[:k], one["_accepted"][:k])
+    np.testing.assert_array_equal(accepted[:k], ref["_accepted"][:k], err_msg=f"{what}: accept / revert mask vs oracle")
+    np.testing.assert_array_equal(accepted[:k], one["_accepted"][:k], err_msg=f"{what}: accept / revert mask vs one GPU")
     acc = np.asarray(ref["_accepted"][:k], dtype=bool)
     bound = np.where(acc, TOL_OBJ_REL, 1e-5)
     rel_ref = np.abs(LL[:k] - ref["_LL"][:k]) / np.abs(ref["_LL"][:k])
@@ -108,19 +109,35 @@ def _oracle(kw):
 def _check_against_one_gpu(res, one, ref):
     from tests.util import principal_angle
     k = None
-    for r in res:       # replicated quantities are identical on every rank
+    for r in res:
         k = _check_trace(r[3], r[4], one, ref, f"rank {r[0]} of {len(res)}")
-        np.testing.assert_array_equal(r[7], res[0][7])
+        # Replicated quantities: every rank computes them from its own copy of the all-reduced products.  Two
+        # ranks get bit-identical copies (a + b = b + a); from four ranks on a sum all-reduce may associate
+        # differently per rank, so the copies agree to rounding, not to the bit (the DECISIONS are bit-identical:
+        # they are taken on max-reduced scalars, fit.cu / tsvd.cu).
+        dU = np.abs(r[7] - res[0][7]).max()
+        assert dU <= (0.0 if len(res) <= 2 else 1e-11), f"U differs between rank {r[0]} and rank 0 by {dU:.2e}"
+        np.testing.assert_array_equal(r[4], res[0][4])
+        np.testing.assert_array_equal(r[3], res[0][3])
     if k < len(ref["_LL"]):
         return          # the runs went past an unreproducible decision: the final factors are not comparable
-    for r in res:
-        np.testing.assert_allclose(r[5], one["alpha"], atol=1e-5)
-        np.testing.assert_allclose(r[9], one["D"], rtol=1e-5)
-        assert principal_angle(r[7], one["U"]) < 1e-4
     beta = np.concatenate([r[6] for r in res])
     V = np.vstack([r[8] for r in res])
-    np.testing.assert_allclose(beta, one["beta"], atol=1e-5)
-    assert principal_angle(V, one["V"]) < 1e-4
+    r = res[0]
+    aU, aV = principal_angle(r[7], one["U"]), principal_angle(V, one["V"])
+    aUo, aVo = principal_angle(r[7], ref["U"]), principal_angle(V, ref["V"])
+    msg = (f"{len(res)} ranks (svd unconverged {r[10]}, worst est {r[11]:.1e}, passes {r[12]}; one GPU: {one['_svd_unconverged']}, "
+           f"{one['_svd_worst_est']:.1e}, {one['_prof']['svd_passes']}): angles vs one GPU U {aU:.2e} V {aV:.2e}; vs oracle U {aUo:.2e} V {aVo:.2e}; one GPU vs oracle U "
+           f"{principal_angle(one['U'], ref['U']):.2e} V {principal_angle(one['V'], ref['V']):.2e}; alpha vs oracle "
+           f"{np.abs(r[5] - ref['alpha']).max():.2e}, D rel {np.abs(r[9] / ref['D'] - 1).max():.2e}")
+    print(msg)
+    # the parity criterion proper: against the oracle, the north-star tolerances
+    assert aUo < 1e-4 and aVo < 1e-4, msg
+    np.testing.assert_allclose(r[5], ref["alpha"], atol=1e-5, err_msg=msg)
+    np.testing.assert_allclose(beta, ref["beta"], atol=1e-5, err_msg=msg)
+    np.testing.assert_allclose(r[9], ref["D"], rtol=1e-5, err_msg=msg)
+    # two runs that are each inside a tolerance of the reference may be twice that apart
+    assert aU < 2e-4 and aV < 2e-4, msg
 
 
 @pytest.mark.parametrize("world,kw", [(2, dict()), (2, dict(infer_beta=True, max_iter=25)), (4, dict(max_iter=40)),
@@ -165,9 +182,15 @@ def _one_caller_body(q, ngpu):
         ref = _oracle(dict(max_iter=40))
         k = _check_trace(many["_LL"], many["_accepted"], one, ref, f"ngpu={ngpu}")
         assert k == len(ref["_LL"]), f"the oracle run has a knife-edge decision at iteration {k + 1}: pick another max_iter"
-        np.testing.assert_allclose(many["alpha"], one["alpha"], atol=1e-5)
-        np.testing.assert_allclose(many["beta"], one["beta"], atol=1e-5)
-        assert principal_angle(many["U"], one["U"]) < 1e-4 and principal_angle(many["V"], one["V"]) < 1e-4
+        aUo, aVo = principal_angle(many["U"], ref["U"]), principal_angle(many["V"], ref["V"])
+        aU, aV = principal_angle(many["U"], one["U"]), principal_angle(many["V"], one["V"])
+        msg = (f"ngpu={ngpu} (svd unconverged {many['_svd_unconverged']}, worst est {many['_svd_worst_est']:.1e}, passes "
+               f"{many['_prof']['svd_passes']}; one GPU {one['_svd_unconverged']}, {one['_svd_worst_est']:.1e}, {one['_prof']['svd_passes']}): "
+               f"angles vs oracle U {aUo:.2e} V {aVo:.2e}; vs one GPU U {aU:.2e} V {aV:.2e}")
+        print(msg)
+        assert aUo < 1e-4 and aVo < 1e-4 and aU < 2e-4 and aV < 2e-4, msg       # oracle: north-star; one GPU: twice that
+        np.testing.assert_allclose(many["alpha"], ref["alpha"], atol=1e-5, err_msg=msg)
+        np.testing.assert_allclose(many["beta"], ref["beta"], atol=1e-5, err_msg=msg)
         assert many["V"].shape == one["V"].shape and many["W"].shape == Y.shape
         np.testing.assert_allclose(many["W"], one["W"], rtol=5e-4)
         np.testing.assert_allclose(many["scores"], many["V"] * many["D"][None, :], rtol=1e-12)
