@@ -117,37 +117,42 @@ Ctx::~Ctx() {
   if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
 }
 
-// Sum over ranks, with the SAME BITS on every rank afterwards.  Everything gene-sided (Krylov bases, Gram matrices,
-// alpha, the objective) is replicated: each rank recomputes it from its own copy of the all-reduced partial products.
-// A sum all-reduce only promises every rank A correctly rounded sum of the contributions; from four ranks on the
-// association order -- hence the last bit -- may differ from rank to rank (two ranks cannot differ: a + b = b + a).
-// A max all-reduce has no such freedom (max is exactly associative), so the sum is followed by one: every rank ends
-// up with the largest of the candidates, bit for bit.  Cost: one more latency-bound collective per site (messages
-// are <= 5 MB).  (Identical inputs turned out to be necessary but not sufficient for identical replicated state:
-// see svd_bcast in tsvd.cu.)
+// One NCCL all-reduce in place.  Ranks that are threads of one process rendezvous on the host first and complete the
+// collective before going on (see InprocGroup above).
+static void nccl_allreduce(Ctx& ctx, double* dev, int64_t n, ncclRedOp_t op) {
+  Comm* comm = ctx.comm;
+  if (comm->group) inproc_arrive(comm);
+  SCGBM_NCCL(nccl().AllReduce(dev, dev, (size_t)n, ncclFloat64, op, comm->comm, ctx.stream));
+  if (comm->group) SCGBM_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+// Sum over ranks.  A sum all-reduce promises every rank A correctly rounded sum of the contributions, not the SAME
+// one: from four ranks on the association order -- hence the last bit -- may differ from rank to rank (two ranks
+// cannot differ: a + b = b + a).  Nothing downstream may therefore assume bit-identical copies:
+//   * host decisions are taken on max-reduced scalars (fit.cu, tsvd.cu) -- max IS exactly associative;
+//   * the replicated state of the SVD, where a last-bit difference is carried forward and amplified, is imposed
+//     from rank 0 (bcast0; svd_bcast in tsvd.cu has the measurement).
+// SCGBM_SUM_MAX=1 (experiments) additionally follows every sum by a max all-reduce of the result, which makes the
+// copies bit-identical at the price of a second latency-bound collective per site; measured on 4 ranks, that alone did
+// not stop the drift (the eigensolver's output differed between GPUs even for bit-identical input).
 void Ctx::allreduce_sum(double* dev, int64_t n) {
   if (!comm || nranks == 1 || n <= 0) return;
-  if (comm->group) inproc_arrive(comm);
-  ProfScope ps(prof, SCGBM_K_COMM, nranks > 2 ? 2 : 1);
-  SCGBM_NCCL(nccl().AllReduce(dev, dev, (size_t)n, ncclFloat64, ncclSum, comm->comm, stream));
-  if (nranks > 2) {
-    if (comm->group) { SCGBM_CUDA(cudaStreamSynchronize(stream)); inproc_arrive(comm); }
-    SCGBM_NCCL(nccl().AllReduce(dev, dev, (size_t)n, ncclFloat64, ncclMax, comm->comm, stream));
-  }
-  if (comm->group) SCGBM_CUDA(cudaStreamSynchronize(stream));
+  static const bool sum_max = getenv("SCGBM_SUM_MAX") != nullptr;
+  ProfScope ps(prof, SCGBM_K_COMM, (sum_max && nranks > 2) ? 2 : 1);
+  nccl_allreduce(*this, dev, n, ncclSum);
+  if (sum_max && nranks > 2) nccl_allreduce(*this, dev, n, ncclMax);
 }
 void Ctx::allreduce_max(double* dev, int64_t n) {
   if (!comm || nranks == 1 || n <= 0) return;
-  if (comm->group) inproc_arrive(comm);
   ProfScope ps(prof, SCGBM_K_COMM, 1);
-  SCGBM_NCCL(nccl().AllReduce(dev, dev, (size_t)n, ncclFloat64, ncclMax, comm->comm, stream));
-  if (comm->group) SCGBM_CUDA(cudaStreamSynchronize(stream));
+  nccl_allreduce(*this, dev, n, ncclMax);
 }
 
 void Ctx::bcast0(double* dev, int64_t n) {
   if (!comm || nranks == 1 || n <= 0) return;
+  ProfScope ps(prof, SCGBM_K_COMM, 1);
   if (rank != 0) SCGBM_CUDA(cudaMemsetAsync(dev, 0, (size_t)n * sizeof(double), stream));
-  allreduce_sum(dev, n);        // x + 0 + ... + 0 is exact in any order
+  nccl_allreduce(*this, dev, n, ncclSum);        // x + 0 + ... + 0 is exact in any order: rank 0's bits everywhere
 }
 
 __global__ void __launch_bounds__(1024) checksum_kernel(int64_t n, const double* __restrict__ x, double* __restrict__ out) {
