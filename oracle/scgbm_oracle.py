@@ -271,6 +271,48 @@ def poisson_glm_irls(Xd, y, offset, tol=1e-8, maxit=100):
     return coef, se, conv, it
 
 
+def poisson_glm_newton(Xd, y, offset, tol=1e-8, maxit=30):
+    """The iteration of the tensor-core projection path (scgbm_b200/csrc/proj_tc.cu), restated in float64 so that
+    its ALGORITHM can be checked against fastglm's (poisson_glm_irls) without a GPU: Newton's method on the same
+    likelihood (IRLS with the canonical link is Newton), started from the null model's MLE
+    theta = (log(sum y / sum exp(offset)), 0, ..) instead of mu = y + 0.1, stopped on the Newton decrement
+    g' H^-1 g / (|dev| + 0.1) < tol -- the predicted form of fastglm's |dev - devold| / (|dev| + 0.1) < tol -- with the
+    step halved when the deviance rises; standard errors from the X'WX of the last solve, as fastglm reports them.
+    Returns (coef, se, converged, n_solves)."""
+    n, p = Xd.shape
+    if y.sum() <= 0:
+        raise FloatingPointError("no counts: handed to the exact iteration")
+    theta = np.zeros(p)
+    theta[0] = np.log(y.sum() / np.exp(offset).sum())
+    theta_prev, dev_prev, solves, halv, se = theta.copy(), 0.0, 0, 0, np.zeros(p)
+    ylogy = np.sum(np.where(y > 0, y * np.log(np.where(y > 0, y, 1.0)), 0.0))
+    for _ in range(4 * maxit):
+        eta = offset + Xd @ theta
+        mu = np.exp(eta)
+        dev = 2.0 * (ylogy - np.sum(y * eta) - np.sum(y - mu))
+        if not np.isfinite(dev):
+            raise FloatingPointError("non-finite deviance")
+        if solves > 0 and dev > dev_prev + 1e-6 * (abs(dev_prev) + 0.1):
+            halv += 1
+            if halv > 12:
+                raise FloatingPointError("step halving exhausted")
+            theta = 0.5 * (theta + theta_prev)
+            continue
+        g = Xd.T @ (y - mu)
+        H = (Xd.T * mu) @ Xd
+        c, low = sla.cho_factor(H, lower=True, check_finite=False)
+        delta = sla.cho_solve((c, low), g, check_finite=False)
+        se = np.sqrt(np.diag(np.linalg.inv(H)))
+        theta_prev, dev_prev, halv = theta.copy(), dev, 0
+        theta = theta + delta
+        solves += 1
+        if float(g @ delta) / (abs(dev) + 0.1) < tol:
+            return theta, se, True, solves
+        if solves >= maxit:
+            break
+    return theta, se, False, solves
+
+
 def gbm_proj_parallel(Y, M, subsample, ncores=1, tol=1e-4, max_iter=100, svd="exact",
                       rng=None, verbose=False, glm_tol=1e-8, _subfit=None):
     """R/fit.R:213-285.  `subsample` scalar -> `rng.choice` (R's sample() stream is
