@@ -610,6 +610,21 @@ def run_proj(name, cfg, args, R):
     flops = Jl * Ik * ((M + 1) * (M + 2) + 4 * (M + 1)) * sweeps * 2.0          # BASELINE.md section 4, FMA = 2 flop
     fails = int(out["_fail"].sum())
     nbytes = float(Yh.nbytes + (Y_sub.nbytes if Y_sub is not None else 0))
+    # the tensor-core path's rider launches in three views: each reads the shard's counts once (u16 unless the shard's
+    # maximum allowed u8: bytes quoted at 2 B, an upper bound), evaluates one exp per entry, and writes nothing I x J
+    tc = out.get("_glm_tc") or {}
+    n_rider = int(tc.get("sweeps", 0)) * int(math.ceil(((M + 1) * (M + 2) / 2 + 1) / 32.0))
+    rider_ms = float(pp["ms"].get("fused", 0.0))
+    views = None
+    if out["_glm_method"] == "tcgen05" and n_rider > 0 and rider_ms > 0:
+        peak_gbs, _src = measured_peak()
+        entries = float(n_rider) * Jl * Ik
+        views = {"rider_launches": n_rider, "rider_ms": rider_ms,
+                 "hbm": {"achieved_gbs": entries * 2.0 / (rider_ms * 1e-3) / 1e9, "peak_gbs": peak_gbs,
+                         "frac": entries * 2.0 / (rider_ms * 1e-3) / 1e9 / peak_gbs if peak_gbs else None},
+                 "exp_per_s": entries / (rider_ms * 1e-3),
+                 "bound": "epilogue issue / SFU, not HBM: every 32-column block of the Khatri-Rao operand re-evaluates the eta tile "
+                          "and the exp (DESIGN.md section 10, item 4: one launch per sweep would cut this 8x)"}
     free_host()
     if rank != 0:
         return None
@@ -622,7 +637,7 @@ def run_proj(name, cfg, args, R):
                                                  "genes_kept": int(Ik), "irls_sweeps_mean": sweeps, "glm_failures": fails}),
         "roofline": {"bound": "tensor", "achieved": flops / (k9_ms * 1e-3) / 1e12, "peak": None, "unit": "TFLOP/s",
                      "frac": None, "traffic": None, "glm_method": out["_glm_method"], "tc": out["_glm_tc"],
-                     "kernel_ms": {k: v for k, v in pp["ms"].items() if v > 0},
+                     "kernel_ms": {k: v for k, v in pp["ms"].items() if v > 0}, "rider_views": views,
                      "note": "K9, rank 0: algorithmic IRLS flops (BASELINE.md section 4, at the mean number of solves per cell) over "
                              "the device time of the projection kernels.  tcgen05 method (proj_tc.cu): all cells in lock step, "
                              "gradient and Hessian of every Newton sweep from ceil((T+1)/32) launches of fused_tc_kernel's product "
